@@ -1,0 +1,631 @@
+// fra_api.cu - the C ABI of libfra.so (include/fra.h): context, control-plane
+// byte decoder, kernel dispatch.  Host code only; kernels are in k1_*.cuh / k2_fft.cuh.
+//
+// Control plane restates NEW/command_control.vhd:46-78 (mode / reset / start),
+// NEW/rx_filter_coeff.vhd:41-66 (0xF1 + 12 bytes, busy), NEW/filter_iir12_cust.vhd:
+// 48-60,83-94 (register map) and IMP/sequ2.vhd:83-96,216 (transport, request).
+#include "../../include/fra.h"
+
+#include "k1_window_iir.cuh"
+#include "k1b_stream.cuh"
+#include "k2_fft.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+namespace {
+
+using namespace fra;
+
+const int16_t kHannRom[kWindowLen] = {
+#include "hann_rom_q15.inc"
+};
+
+// IMP/filter_pkg.vhd:54-68 in the register order of NEW/filter_iir12_cust.vhd:83-94
+const int8_t kBank0[12] = {-14, 0, 14, 107, 21, 127, -15, 0, 15, 107, -21, 127};
+
+constexpr int kLaneMinChannels = 148 * 4 * 32;   // below this k1_lane cannot fill the SMs' schedulers
+
+}  // namespace
+
+struct fra_ctx {
+    int device = 0;
+    int channels = 0;
+    int n = 0;
+    int log2n = 0;
+    unsigned flags = 0;
+    int sm_count = 0;
+
+    // control plane (what the RTL keeps in registers)
+    uint8_t mode = FRA_MODE_BYPASS;
+    uint8_t transport = FRA_CMD_ETHERNET_MODE;
+    int8_t bank1[12] = {0};
+    int upload_pos = -1;            // >= 0: inside a 0xF1 upload, bytes received so far
+    int8_t upload_buf[12] = {0};
+    uint64_t n_start = 0, n_request = 0, n_reset = 0, n_upload = 0;
+
+    // device resources
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_streams[3] = {nullptr, nullptr, nullptr};
+    int *d_rom32 = nullptr;
+    int16_t *d_state = nullptr;       // [C][6][4]
+    int16_t *d_scratch = nullptr;     // [C][N] filter output when the caller does not ask for it
+    float2 *d_tw1 = nullptr, *d_tw2 = nullptr, *d_twn = nullptr;
+    // staging for fra_process_host
+    int16_t *d_in = nullptr;
+    uint8_t *d_frames = nullptr;
+    int16_t *d_filtered_out = nullptr;
+    float *d_iq = nullptr, *d_mag = nullptr, *d_phase = nullptr;
+    // K1b work space
+    int16_t *d_entry = nullptr, *d_exit = nullptr;
+    int *d_flags = nullptr, *d_counts = nullptr;
+    int k1b_capacity = 0;
+
+    int last_kernels = 0;
+    char err[256] = {0};
+};
+
+namespace {
+
+int fail_cuda(fra_ctx *ctx, cudaError_t e, const char *what)
+{
+    if (ctx) std::snprintf(ctx->err, sizeof(ctx->err), "%s: %s", what, cudaGetErrorString(e));
+    return FRA_ERR_CUDA;
+}
+
+#define FRA_TRY(ctx, expr)                                         \
+    do {                                                           \
+        cudaError_t e_ = (expr);                                   \
+        if (e_ != cudaSuccess) return fail_cuda((ctx), e_, #expr); \
+    } while (0)
+
+StageCoef make_stage(const int8_t *k)       // k = B0,B1,B2,A0,A1 (NEW/filter_iir_cust.vhd:104-108)
+{
+    StageCoef c;
+    c.b0 = (float)k[0] / 128.0f;
+    c.b1 = (float)k[1] / 128.0f;
+    c.b2 = (float)k[2] / 128.0f;
+    c.na0 = -(float)k[3] / 128.0f;
+    c.na1 = -(float)k[4] / 128.0f;
+    return c;
+}
+
+CascadeCoef make_cascade(const int8_t coeff12[12])
+{
+    CascadeCoef c;
+    c.set[0] = make_stage(coeff12);          // ALPHA: bytes 0..4
+    c.set[1] = make_stage(coeff12 + 6);      // BETA: bytes 6..10 (bytes 5, 11 = A2 are unconnected)
+    return c;
+}
+
+void do_reset(fra_ctx *ctx)
+{
+    // rst_n pulse: NEW/command_control.vhd:50, NEW/filter_iir12_cust.vhd:51-52, IMP/sequ2.vhd:86
+    ctx->mode = FRA_MODE_BYPASS;
+    std::memset(ctx->bank1, 0, sizeof(ctx->bank1));
+    ctx->transport = FRA_CMD_ETHERNET_MODE;
+    ctx->n_reset++;
+}
+
+template <int LOG2N, bool WIN, int QMODE>
+int launch_k2_inst(fra_ctx *ctx, const K2Args &args, cudaStream_t st)
+{
+    using P = FftPlan<LOG2N>;
+    auto kfn = k2_fft<LOG2N, WIN, QMODE>;
+    FRA_TRY(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, P::SMEM_BYTES));
+    const int grid = (args.batch + P::FPC - 1) / P::FPC;
+    if (grid > 0) {
+        FRA_LAUNCH(kfn, dim3(grid), dim3(P::THREADS), (size_t)P::SMEM_BYTES, st, args);
+        FRA_TRY(ctx, cudaGetLastError());
+        ctx->last_kernels++;
+    }
+    return FRA_OK;
+}
+
+template <int LOG2N>
+int launch_k2_n(fra_ctx *ctx, const K2Args &args, bool win, int qmode, cudaStream_t st)
+{
+    if (win) {
+        if (qmode == 0) return launch_k2_inst<LOG2N, true, 0>(ctx, args, st);
+        if (qmode == 1) return launch_k2_inst<LOG2N, true, 1>(ctx, args, st);
+        return launch_k2_inst<LOG2N, true, 2>(ctx, args, st);
+    }
+    if (qmode == 0) return launch_k2_inst<LOG2N, false, 0>(ctx, args, st);
+    if (qmode == 1) return launch_k2_inst<LOG2N, false, 1>(ctx, args, st);
+    return launch_k2_inst<LOG2N, false, 2>(ctx, args, st);
+}
+
+int launch_k2(fra_ctx *ctx, const K2Args &args, bool win, int qmode, cudaStream_t st)
+{
+    switch (ctx->log2n) {
+    case 10: return launch_k2_n<10>(ctx, args, win, qmode, st);
+    case 11: return launch_k2_n<11>(ctx, args, win, qmode, st);
+    case 12: return launch_k2_n<12>(ctx, args, win, qmode, st);
+    case 13: return launch_k2_n<13>(ctx, args, win, qmode, st);
+    case 14: return launch_k2_n<14>(ctx, args, win, qmode, st);
+    case 15: return launch_k2_n<15>(ctx, args, win, qmode, st);
+    default: return FRA_ERR_UNSUPPORTED;
+    }
+}
+
+// One step over channels [c0, c0 + nch): pointers in `o` and d_in are already
+// offset to channel c0.
+int process_range(fra_ctx *ctx, const int16_t *d_in, int c0, int nch, int continuous, int log2_scale,
+                  const fra_outputs &o, cudaStream_t st)
+{
+    const int n = ctx->n;
+    const bool iir = (ctx->mode == FRA_MODE_BANK0 || ctx->mode == FRA_MODE_BANK1);
+    const bool want_fft = o.d_frames || o.d_iq || o.d_mag || o.d_phase;
+    const int16_t *fft_in = d_in;
+
+    if (iir) {
+        int16_t *filt = o.d_filtered ? o.d_filtered : (ctx->d_scratch + (size_t)c0 * n);
+        K1Args k1;
+        k1.in = d_in;
+        k1.out = filt;
+        k1.state = ctx->d_state + (size_t)c0 * 24;
+        k1.rom32 = ctx->d_rom32;
+        k1.coef = make_cascade(ctx->mode == FRA_MODE_BANK0 ? kBank0 : ctx->bank1);
+        k1.channels = nch;
+        k1.n = n;
+        k1.continuous = continuous;
+        bool split = nch < kLaneMinChannels;
+        if (ctx->flags & FRA_K1_FORCE_LANE) split = false;
+        if (ctx->flags & FRA_K1_FORCE_SPLIT) split = true;
+        if (split) {
+            const int per_cta = kSplitWarps * kSplitGroups;
+            const int grid = (nch + per_cta - 1) / per_cta;
+            const size_t smem = (size_t)kSplitWarps * kSplitSmemPerWarp;
+            auto kfn = k1_split;
+            FRA_TRY(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            FRA_LAUNCH(kfn, dim3(grid), dim3(kSplitWarps * 32), smem, st, k1);
+        } else {
+            const int grid = (nch + kLaneBlock - 1) / kLaneBlock;
+            auto kfn = k1_lane;
+            FRA_LAUNCH(kfn, dim3(grid), dim3(kLaneBlock), (size_t)0, st, k1);
+        }
+        FRA_TRY(ctx, cudaGetLastError());
+        ctx->last_kernels++;
+        fft_in = filt;
+    } else if (o.d_filtered) {
+        const size_t total8 = (size_t)nch * n / 8;
+        auto kfn = k1_window_only;
+        FRA_LAUNCH(kfn, dim3((unsigned)((total8 + 255) / 256)), dim3(256), (size_t)0, st, d_in, o.d_filtered,
+                   (const int *)ctx->d_rom32, total8, n);
+        FRA_TRY(ctx, cudaGetLastError());
+        ctx->last_kernels++;
+    }
+
+    if (want_fft) {
+        K2Args k2;
+        k2.in = reinterpret_cast<const uint32_t *>(fft_in);
+        k2.rom32 = ctx->d_rom32;
+        k2.tw1 = ctx->d_tw1;
+        k2.tw2 = ctx->d_tw2;
+        k2.twn = ctx->d_twn;
+        k2.frames = reinterpret_cast<uint32_t *>(o.d_frames);
+        k2.iq = reinterpret_cast<float2 *>(o.d_iq);
+        k2.mag = o.d_mag;
+        k2.phase = o.d_phase;
+        k2.qscale = std::ldexp(0.5f, log2_scale);
+        k2.batch = nch;
+        const bool nearest = (ctx->flags & FRA_ROUND_NEAREST) != 0;
+        const int qmode = nearest ? 2 : (log2_scale <= -ctx->log2n ? 0 : 1);
+        int rc = launch_k2(ctx, k2, /*win=*/!iir, qmode, st);
+        if (rc != FRA_OK) return rc;
+    }
+    return FRA_OK;
+}
+
+fra_outputs offset_outputs(const fra_outputs &o, size_t c0, int n)
+{
+    fra_outputs r = o;
+    if (r.d_filtered) r.d_filtered += c0 * n;
+    if (r.d_frames) r.d_frames += c0 * n * 4;
+    if (r.d_iq) r.d_iq += c0 * n * 2;
+    if (r.d_mag) r.d_mag += c0 * n;
+    if (r.d_phase) r.d_phase += c0 * n;
+    return r;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fra_abi_version(void) { return FRA_ABI_VERSION; }
+
+const char *fra_strerror(int status)
+{
+    switch (status) {
+    case FRA_OK: return "ok";
+    case FRA_ERR_INVALID: return "invalid argument";
+    case FRA_ERR_NO_DEVICE: return "no CUDA device (libfra has no CPU fallback)";
+    case FRA_ERR_CUDA: return "CUDA error";
+    case FRA_ERR_NOMEM: return "out of memory";
+    case FRA_ERR_UNSUPPORTED: return "unsupported configuration";
+    case FRA_ERR_BUSY: return "byte stream ended inside a 0xF1 coefficient upload";
+    default: return "unknown status";
+    }
+}
+
+int fra_window_rom(int16_t out[FRA_WINDOW_LEN])
+{
+    if (!out) return FRA_ERR_INVALID;
+    std::memcpy(out, kHannRom, sizeof(kHannRom));
+    return FRA_OK;
+}
+
+int fra_create(fra_ctx **out, int device, int n_channels, int fft_size, unsigned flags)
+{
+    if (!out) return FRA_ERR_INVALID;
+    *out = nullptr;
+    if (n_channels <= 0) return FRA_ERR_INVALID;
+    int log2n = 0;
+    while ((1 << log2n) < fft_size) ++log2n;
+    if ((1 << log2n) != fft_size) return FRA_ERR_INVALID;
+    if (log2n < 10 || log2n > 15) return FRA_ERR_UNSUPPORTED;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return FRA_ERR_NO_DEVICE;
+    if (device < 0 || device >= count) return FRA_ERR_INVALID;
+
+    fra_ctx *ctx = new (std::nothrow) fra_ctx();
+    if (!ctx) return FRA_ERR_NOMEM;
+    ctx->device = device;
+    ctx->channels = n_channels;
+    ctx->n = fft_size;
+    ctx->log2n = log2n;
+    ctx->flags = flags;
+
+    auto bail = [&](int rc) { fra_destroy(ctx); return rc; };
+    if (cudaSetDevice(device) != cudaSuccess) return bail(FRA_ERR_NO_DEVICE);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(FRA_ERR_NO_DEVICE);
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(FRA_ERR_CUDA);
+    for (auto &s : ctx->copy_streams)
+        if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return bail(FRA_ERR_CUDA);
+
+    const size_t n = (size_t)fft_size;
+    if (cudaMalloc((void **)&ctx->d_rom32, kWindowLen * sizeof(int)) != cudaSuccess) return bail(FRA_ERR_NOMEM);
+    if (cudaMalloc((void **)&ctx->d_state, (size_t)n_channels * 24 * sizeof(int16_t)) != cudaSuccess) return bail(FRA_ERR_NOMEM);
+    if (cudaMalloc((void **)&ctx->d_tw1, 256 * sizeof(float2)) != cudaSuccess) return bail(FRA_ERR_NOMEM);
+    if (cudaMalloc((void **)&ctx->d_tw2, 4096 * sizeof(float2)) != cudaSuccess) return bail(FRA_ERR_NOMEM);
+    if (cudaMalloc((void **)&ctx->d_twn, (n / 2) * sizeof(float2)) != cudaSuccess) return bail(FRA_ERR_NOMEM);
+
+    std::vector<int> rom32(kWindowLen);
+    for (int i = 0; i < kWindowLen; ++i) rom32[i] = kHannRom[i];
+    std::vector<float2> tw1(256), tw2(4096), twn(n / 2);
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int r = 0; r < 16; ++r)
+        for (int k = 0; k < 16; ++k) {
+            double a = -two_pi * (double)(r * k) / 256.0;
+            tw1[r * 16 + k] = make_float2((float)std::cos(a), (float)std::sin(a));
+        }
+    for (int r = 0; r < 16; ++r)
+        for (int k = 0; k < 256; ++k) {
+            double a = -two_pi * (double)(r * k) / 4096.0;
+            tw2[r * 256 + k] = make_float2((float)std::cos(a), (float)std::sin(a));
+        }
+    for (size_t e = 0; e < n / 2; ++e) {
+        double a = -two_pi * (double)e / (double)n;
+        twn[e] = make_float2((float)std::cos(a), (float)std::sin(a));
+    }
+    if (cudaMemcpy(ctx->d_rom32, rom32.data(), rom32.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(ctx->d_tw1, tw1.data(), tw1.size() * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(ctx->d_tw2, tw2.data(), tw2.size() * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(ctx->d_twn, twn.data(), twn.size() * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemset(ctx->d_state, 0, (size_t)n_channels * 24 * sizeof(int16_t)) != cudaSuccess)
+        return bail(FRA_ERR_CUDA);
+    *out = ctx;
+    return FRA_OK;
+}
+
+int fra_destroy(fra_ctx *ctx)
+{
+    if (!ctx) return FRA_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    void *bufs[] = {ctx->d_rom32, ctx->d_state, ctx->d_scratch, ctx->d_tw1, ctx->d_tw2, ctx->d_twn, ctx->d_in,
+                    ctx->d_frames, ctx->d_filtered_out, ctx->d_iq, ctx->d_mag, ctx->d_phase, ctx->d_entry,
+                    ctx->d_exit, ctx->d_flags, ctx->d_counts};
+    for (void *p : bufs)
+        if (p) cudaFree(p);
+    for (auto s : ctx->copy_streams)
+        if (s) cudaStreamDestroy(s);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return FRA_OK;
+}
+
+int fra_command(fra_ctx *ctx, const uint8_t *bytes, size_t n)
+{
+    if (!ctx || (!bytes && n)) return FRA_ERR_INVALID;
+    for (size_t i = 0; i < n; ++i) {
+        const uint8_t b = bytes[i];
+        if (ctx->upload_pos >= 0) {                       // ACQUIRE: every byte is a coefficient
+            ctx->upload_buf[ctx->upload_pos++] = (int8_t)b;
+            if (ctx->upload_pos == 12) {
+                std::memcpy(ctx->bank1, ctx->upload_buf, 12);
+                ctx->upload_pos = -1;
+                ctx->n_upload++;
+            }
+            continue;
+        }
+        switch (b) {
+        case FRA_CMD_FILTER_UPDATE: ctx->upload_pos = 0; break;
+        case FRA_MODE_BANK0:
+        case FRA_MODE_BANK1:
+        case FRA_MODE_BYPASS: ctx->mode = b; break;
+        case FRA_CMD_RESET: {
+            int rc = fra_reset(ctx);
+            if (rc != FRA_OK) return rc;
+            break;
+        }
+        case FRA_CMD_START: ctx->n_start++; break;
+        case FRA_CMD_UART_REQUEST: ctx->n_request++; break;
+        case FRA_CMD_ETHERNET_MODE:
+        case FRA_CMD_UART_MODE: ctx->transport = b; break;
+        default: break;                                   // matches no decoder branch: dropped
+        }
+    }
+    return ctx->upload_pos >= 0 ? FRA_ERR_BUSY : FRA_OK;
+}
+
+int fra_load_bank1(fra_ctx *ctx, const int8_t coeff[12])
+{
+    if (!ctx || !coeff) return FRA_ERR_INVALID;
+    std::memcpy(ctx->bank1, coeff, 12);
+    ctx->n_upload++;
+    return FRA_OK;
+}
+
+int fra_set_mode(fra_ctx *ctx, uint8_t mode)
+{
+    if (!ctx) return FRA_ERR_INVALID;
+    if (mode != FRA_MODE_BANK0 && mode != FRA_MODE_BANK1 && mode != FRA_MODE_BYPASS) return FRA_ERR_INVALID;
+    ctx->mode = mode;
+    return FRA_OK;
+}
+
+int fra_reset(fra_ctx *ctx)
+{
+    if (!ctx) return FRA_ERR_INVALID;
+    do_reset(ctx);
+    FRA_TRY(ctx, cudaSetDevice(ctx->device));
+    // synchronous: a reset must be ordered before work on ANY stream the caller uses next
+    FRA_TRY(ctx, cudaMemsetAsync(ctx->d_state, 0, (size_t)ctx->channels * 24 * sizeof(int16_t), ctx->stream));
+    FRA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return FRA_OK;
+}
+
+int fra_get_mode(const fra_ctx *ctx, uint8_t *mode)
+{
+    if (!ctx || !mode) return FRA_ERR_INVALID;
+    *mode = ctx->mode;
+    return FRA_OK;
+}
+
+int fra_get_bank(const fra_ctx *ctx, int bank, int8_t coeff[12])
+{
+    if (!ctx || !coeff || (bank != 0 && bank != 1)) return FRA_ERR_INVALID;
+    std::memcpy(coeff, bank == 0 ? kBank0 : ctx->bank1, 12);
+    return FRA_OK;
+}
+
+int fra_get_transport(const fra_ctx *ctx, uint8_t *transport)
+{
+    if (!ctx || !transport) return FRA_ERR_INVALID;
+    *transport = ctx->transport;
+    return FRA_OK;
+}
+
+int fra_get_counters(const fra_ctx *ctx, uint64_t *n_start, uint64_t *n_request, uint64_t *n_reset, uint64_t *n_upload)
+{
+    if (!ctx) return FRA_ERR_INVALID;
+    if (n_start) *n_start = ctx->n_start;
+    if (n_request) *n_request = ctx->n_request;
+    if (n_reset) *n_reset = ctx->n_reset;
+    if (n_upload) *n_upload = ctx->n_upload;
+    return FRA_OK;
+}
+
+int fra_process(fra_ctx *ctx, const int16_t *d_in, int continuous, int log2_scale, const fra_outputs *out,
+                void *cuda_stream)
+{
+    if (!ctx || !d_in || !out) return FRA_ERR_INVALID;
+    if (log2_scale == FRA_SCALE_DEFAULT) log2_scale = -ctx->log2n;
+    if (log2_scale < -40 || log2_scale > 16) return FRA_ERR_INVALID;
+    FRA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    const bool iir = (ctx->mode == FRA_MODE_BANK0 || ctx->mode == FRA_MODE_BANK1);
+    if (iir && !out->d_filtered && !ctx->d_scratch)
+        if (cudaMalloc((void **)&ctx->d_scratch, (size_t)ctx->channels * ctx->n * sizeof(int16_t)) != cudaSuccess)
+            return FRA_ERR_NOMEM;
+    ctx->last_kernels = 0;
+    return process_range(ctx, d_in, 0, ctx->channels, continuous, log2_scale, *out, st);
+}
+
+int fra_process_host(fra_ctx *ctx, const int16_t *h_in, int continuous, int log2_scale, const fra_outputs *h_out)
+{
+    if (!ctx || !h_in || !h_out) return FRA_ERR_INVALID;
+    if (log2_scale == FRA_SCALE_DEFAULT) log2_scale = -ctx->log2n;
+    if (log2_scale < -40 || log2_scale > 16) return FRA_ERR_INVALID;
+    FRA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t C = (size_t)ctx->channels, n = (size_t)ctx->n;
+    auto need = [&](void **p, size_t bytes) -> bool { return *p || cudaMalloc(p, bytes) == cudaSuccess; };
+    if (!need((void **)&ctx->d_in, C * n * 2)) return FRA_ERR_NOMEM;
+    if (h_out->d_frames && !need((void **)&ctx->d_frames, C * n * 4)) return FRA_ERR_NOMEM;
+    if (h_out->d_filtered && !need((void **)&ctx->d_filtered_out, C * n * 2)) return FRA_ERR_NOMEM;
+    if (h_out->d_iq && !need((void **)&ctx->d_iq, C * n * 8)) return FRA_ERR_NOMEM;
+    if (h_out->d_mag && !need((void **)&ctx->d_mag, C * n * 4)) return FRA_ERR_NOMEM;
+    if (h_out->d_phase && !need((void **)&ctx->d_phase, C * n * 4)) return FRA_ERR_NOMEM;
+    const bool iir = (ctx->mode == FRA_MODE_BANK0 || ctx->mode == FRA_MODE_BANK1);
+    if (iir && !h_out->d_filtered && !need((void **)&ctx->d_scratch, C * n * 2)) return FRA_ERR_NOMEM;
+
+    fra_outputs dev;
+    dev.d_filtered = h_out->d_filtered ? ctx->d_filtered_out : nullptr;
+    dev.d_frames = h_out->d_frames ? ctx->d_frames : nullptr;
+    dev.d_iq = h_out->d_iq ? ctx->d_iq : nullptr;
+    dev.d_mag = h_out->d_mag ? ctx->d_mag : nullptr;
+    dev.d_phase = h_out->d_phase ? ctx->d_phase : nullptr;
+
+    // pending control-plane work (a reset's memset) is ordered on ctx->stream
+    FRA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->last_kernels = 0;
+    // channel slices round-robin over three streams: H2D(i+1) and D2H(i-1) overlap compute(i)
+    const int n_slices = (int)std::min<size_t>(C, C * n >= ((size_t)1 << 24) ? 8 : 1);
+    const size_t per = (C + n_slices - 1) / n_slices;
+    int rc = FRA_OK;
+    for (int s = 0; s < n_slices && rc == FRA_OK; ++s) {
+        const size_t c0 = (size_t)s * per;
+        if (c0 >= C) break;
+        const size_t nch = std::min(per, C - c0);
+        cudaStream_t st = ctx->copy_streams[s % 3];
+        FRA_TRY(ctx, cudaMemcpyAsync(ctx->d_in + c0 * n, h_in + c0 * n, nch * n * 2, cudaMemcpyHostToDevice, st));
+        fra_outputs o = offset_outputs(dev, c0, (int)n);
+        rc = process_range(ctx, ctx->d_in + c0 * n, (int)c0, (int)nch, continuous, log2_scale, o, st);
+        if (rc != FRA_OK) break;
+        if (h_out->d_filtered)
+            FRA_TRY(ctx, cudaMemcpyAsync(h_out->d_filtered + c0 * n, o.d_filtered, nch * n * 2, cudaMemcpyDeviceToHost, st));
+        if (h_out->d_frames)
+            FRA_TRY(ctx, cudaMemcpyAsync(h_out->d_frames + c0 * n * 4, o.d_frames, nch * n * 4, cudaMemcpyDeviceToHost, st));
+        if (h_out->d_iq)
+            FRA_TRY(ctx, cudaMemcpyAsync(h_out->d_iq + c0 * n * 2, o.d_iq, nch * n * 8, cudaMemcpyDeviceToHost, st));
+        if (h_out->d_mag)
+            FRA_TRY(ctx, cudaMemcpyAsync(h_out->d_mag + c0 * n, o.d_mag, nch * n * 4, cudaMemcpyDeviceToHost, st));
+        if (h_out->d_phase)
+            FRA_TRY(ctx, cudaMemcpyAsync(h_out->d_phase + c0 * n, o.d_phase, nch * n * 4, cudaMemcpyDeviceToHost, st));
+    }
+    for (auto st : ctx->copy_streams) {
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess && rc == FRA_OK) rc = fail_cuda(ctx, e, "cudaStreamSynchronize");
+    }
+    return rc;
+}
+
+int fra_get_state(fra_ctx *ctx, int16_t *d_state, void *cuda_stream)
+{
+    if (!ctx || !d_state) return FRA_ERR_INVALID;
+    FRA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    FRA_TRY(ctx, cudaMemcpyAsync(d_state, ctx->d_state, (size_t)ctx->channels * 24 * sizeof(int16_t),
+                                 cudaMemcpyDeviceToDevice, st));
+    return FRA_OK;
+}
+
+int fra_set_state(fra_ctx *ctx, const int16_t *d_state, void *cuda_stream)
+{
+    if (!ctx || !d_state) return FRA_ERR_INVALID;
+    FRA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    FRA_TRY(ctx, cudaMemcpyAsync(ctx->d_state, d_state, (size_t)ctx->channels * 24 * sizeof(int16_t),
+                                 cudaMemcpyDeviceToDevice, st));
+    return FRA_OK;
+}
+
+int fra_iir_stream(fra_ctx *ctx, const int16_t *d_in, int16_t *d_out, size_t n, int continuous, int *n_rerun)
+{
+    if (!ctx || !d_in || !d_out || n == 0 || (n % 8) != 0) return FRA_ERR_INVALID;
+    FRA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int chunk = 4096, warm = 2048;
+    const int n_chunks = (int)((n + chunk - 1) / chunk);
+    if (n_chunks > ctx->k1b_capacity) {
+        void *old[] = {ctx->d_entry, ctx->d_exit, ctx->d_flags};
+        for (void *p : old)
+            if (p) cudaFree(p);
+        ctx->d_entry = ctx->d_exit = nullptr;
+        ctx->d_flags = nullptr;
+        ctx->k1b_capacity = 0;
+        if (cudaMalloc((void **)&ctx->d_entry, (size_t)n_chunks * 24 * sizeof(int16_t)) != cudaSuccess ||
+            cudaMalloc((void **)&ctx->d_exit, (size_t)n_chunks * 24 * sizeof(int16_t)) != cudaSuccess ||
+            cudaMalloc((void **)&ctx->d_flags, (size_t)n_chunks * sizeof(int)) != cudaSuccess)
+            return FRA_ERR_NOMEM;
+        ctx->k1b_capacity = n_chunks;
+    }
+    if (!ctx->d_counts && cudaMalloc((void **)&ctx->d_counts, 2 * sizeof(int)) != cudaSuccess) return FRA_ERR_NOMEM;
+    cudaStream_t st = ctx->stream;
+    const bool iir = (ctx->mode == FRA_MODE_BANK0 || ctx->mode == FRA_MODE_BANK1);
+    K1bArgs a;
+    a.in = d_in;
+    a.out = d_out;
+    a.rom32 = ctx->d_rom32;
+    a.coef = make_cascade(ctx->mode == FRA_MODE_BANK1 ? ctx->bank1 : kBank0);
+    a.entry = ctx->d_entry;
+    a.exit_ = ctx->d_exit;
+    a.state0 = ctx->d_state;
+    a.flags = ctx->d_flags;
+    a.n_bad = ctx->d_counts;
+    a.n = n;
+    a.chunk = chunk;
+    a.warm = warm;
+    a.n_chunks = n_chunks;
+    a.continuous = continuous;
+    a.apply_window = 1;
+    a.iir = iir ? 1 : 0;
+    ctx->last_kernels = 0;
+    FRA_TRY(ctx, cudaMemsetAsync(ctx->d_counts, 0, 2 * sizeof(int), st));
+    {
+        auto kfn = k1b_speculate;
+        FRA_LAUNCH(kfn, dim3((n_chunks + 63) / 64), dim3(64), (size_t)0, st, a);
+        FRA_TRY(ctx, cudaGetLastError());
+        auto vfn = k1b_verify;
+        FRA_LAUNCH(vfn, dim3((n_chunks + 127) / 128), dim3(128), (size_t)0, st, a);
+        FRA_TRY(ctx, cudaGetLastError());
+        ctx->last_kernels += 2;
+    }
+    int counts[2] = {0, 0};
+    FRA_TRY(ctx, cudaMemcpyAsync(counts, ctx->d_counts, sizeof(counts), cudaMemcpyDeviceToHost, st));
+    FRA_TRY(ctx, cudaStreamSynchronize(st));
+    if (counts[0] > 0) {
+        auto rfn = k1b_repair;
+        FRA_LAUNCH(rfn, dim3(1), dim3(32), (size_t)0, st, a, ctx->d_counts + 1);
+        FRA_TRY(ctx, cudaGetLastError());
+        ctx->last_kernels++;
+        FRA_TRY(ctx, cudaMemcpyAsync(counts, ctx->d_counts, sizeof(counts), cudaMemcpyDeviceToHost, st));
+        FRA_TRY(ctx, cudaStreamSynchronize(st));
+    }
+    // the stream's end state becomes channel 0's history (continuous operation)
+    FRA_TRY(ctx, cudaMemcpyAsync(ctx->d_state, ctx->d_exit + (size_t)(n_chunks - 1) * 24, 24 * sizeof(int16_t),
+                                 cudaMemcpyDeviceToDevice, st));
+    FRA_TRY(ctx, cudaStreamSynchronize(st));
+    if (n_rerun) *n_rerun = counts[1];
+    return FRA_OK;
+}
+
+int fra_fft_only(fra_ctx *ctx, const int16_t *d_in, int batch, float *d_iq, void *cuda_stream)
+{
+    if (!ctx || !d_in || !d_iq || batch <= 0) return FRA_ERR_INVALID;
+    FRA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    K2Args k2;
+    k2.in = reinterpret_cast<const uint32_t *>(d_in);
+    k2.rom32 = ctx->d_rom32;
+    k2.tw1 = ctx->d_tw1;
+    k2.tw2 = ctx->d_tw2;
+    k2.twn = ctx->d_twn;
+    k2.frames = nullptr;
+    k2.iq = reinterpret_cast<float2 *>(d_iq);
+    k2.mag = nullptr;
+    k2.phase = nullptr;
+    k2.qscale = std::ldexp(0.5f, -ctx->log2n);
+    k2.batch = batch;
+    ctx->last_kernels = 0;
+    return launch_k2(ctx, k2, /*win=*/false, /*qmode=*/0, st);
+}
+
+int fra_sync(fra_ctx *ctx)
+{
+    if (!ctx) return FRA_ERR_INVALID;
+    FRA_TRY(ctx, cudaSetDevice(ctx->device));
+    FRA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return FRA_OK;
+}
+
+int fra_last_kernel_count(const fra_ctx *ctx) { return ctx ? ctx->last_kernels : FRA_ERR_INVALID; }
+
+const char *fra_last_cuda_error(const fra_ctx *ctx) { return ctx ? ctx->err : "null context"; }
+
+}  // extern "C"

@@ -1,0 +1,114 @@
+// fra_common.cuh - shared definitions of the libfra kernels (sm_100a).
+//
+// The arithmetic contract (bit-exact window + biquad cascade) is described in
+// DESIGN.md section 3; reference line numbers are given at each primitive.
+#pragma once
+
+#ifdef FRA_HOST_EMUL
+// tests/emul only: the same sources compiled as C++ on host threads (cusim.h).
+#include "cusim.h"
+#define FRA_DYN_SMEM(name) unsigned char *name = cusim::g_dyn_smem
+#define FRA_LAUNCH(kfn, grid, block, smem, stream, ...) \
+    cusim::launch((grid), (block), (smem), [&] { kfn(__VA_ARGS__); })
+#else
+#include <cuda_runtime.h>
+#define FRA_DYN_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
+#define FRA_LAUNCH(kfn, grid, block, smem, stream, ...) \
+    kfn<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+
+#include <stdint.h>
+
+#define FRA_DEV __device__ __forceinline__
+
+namespace fra {
+
+constexpr int kWindowLen = 16384;          // NEW/hann.vhd: Hann_ROM(0 to 16383)
+constexpr int kStages = 6;                 // NEW/filter_iir12_cust.vhd:68-240
+constexpr float kMagic = 12582912.0f;      // 1.5 * 2^23: ulp = 1 on [2^23, 2^24)
+constexpr float kMagicB = 12615680.0f;     // kMagic + 2^15 (offset-binary accumulator)
+constexpr float kBias16 = 8421376.0f;      // 2^23 + 2^15
+
+// Per-stage coefficients prepared on the host from the 12 int8 registers:
+// products on the FP32 pipe, exactly.  |v*c| <= 2^22 fits the 24-bit significand,
+// c/128 is exact, and an FFMA rounds once, so
+//   fma.rm(v, c/128, acc)  = acc + floor(v*c/128)      (acc integer, ulp 1)
+//   fma.rp(v, -c/128, acc) = acc - floor(v*c/128)
+// which is mult(22 downto 7) of NEW/filter_iir_cust.vhd:96-100 up to the 16-bit
+// wrap; the wrap is applied once to the sum (two's-complement addition commutes
+// with it), by taking the low 16 bits of the accumulator's bit pattern.
+struct StageCoef {
+    float b2, b1, b0;    //  B2/128 -> x[n],  B1/128 -> x[n-1],  B0/128 -> x[n-2]
+    float na0, na1;      // -A0/128 -> y[n-2], -A1/128 -> y[n-1]
+};
+
+struct CascadeCoef {
+    StageCoef set[2];    // set 0 (ALPHA): stages 1,3,5; set 1 (BETA): stages 2,4,6
+};
+
+struct StageState {      // registers ve(1), ve(2), vs(1), vs(2) as exact floats
+    float x1, x2, y1, y2;
+};
+
+// The biquad accumulator starts at kMagicB = 1.5*2^23 + 2^15, so the low 16 bits
+// of its bit pattern hold (sum + 32768) mod 2^16: the 16-bit wrapped sum in
+// offset-binary.  One PRMT splices those 16 bits under the exponent of 2^23 and
+// one FADD removes 2^23 + 2^15: the wrapped int16 as an exact float, with no
+// integer<->float conversion on the recurrence.
+FRA_DEV float wrap16_to_float(float acc)
+{
+    unsigned bits = __float_as_uint(acc);
+    return __uint_as_float(__byte_perm(bits, 0x4B000000u, 0x7610)) - kBias16;
+}
+
+// low 16 bits of the accumulator as two's complement (undo the offset-binary)
+FRA_DEV unsigned acc_to_u16(float acc) { return (__float_as_uint(acc) ^ 0x8000u) & 0xFFFFu; }
+
+// One biquad evaluation, NEW/filter_iir_cust.vhd:96-118 + :133-194 (state shift).
+// Returns the accumulator; *y_out gets the wrapped value as a float.  The y[n-1]
+// term is last: it is the only term on the sample-to-sample recurrence.
+FRA_DEV float biquad_step(float x, const StageCoef &k, StageState &s, float *y_out)
+{
+    float acc = __fmaf_rd(s.x2, k.b0, kMagicB);
+    acc = __fmaf_rd(s.x1, k.b1, acc);
+    acc = __fmaf_rd(x, k.b2, acc);
+    acc = __fmaf_ru(s.y2, k.na0, acc);
+    acc = __fmaf_ru(s.y1, k.na1, acc);
+    float y = wrap16_to_float(acc);
+    s.x2 = s.x1; s.x1 = x;
+    s.y2 = s.y1; s.y1 = y;
+    *y_out = y;
+    return acc;
+}
+
+// hann_window arithmetic, NEW/hann8192.vhd:36-39: 32-bit product, +2^14, >>15 is
+// product(31 downto 15) + product(14); numeric_std resize keeps sign + low 15
+// bits, so the only out-of-range value (+32768 for x = c = -32768) becomes 0.
+FRA_DEV int window_int(int x, int c)
+{
+    int v = (x * c + 16384) >> 15;
+    return v == 32768 ? 0 : v;
+}
+
+// int in [-32768, 32767] -> float without the conversion pipe
+FRA_DEV float small_int_to_float(int v)
+{
+    return (float)v;     // 32-bit source: I2FP.F32.S32 (ALU pipe), not the 16-bit I2F of the conversion unit
+}
+
+// two packed int16 (little-endian pair) -> ints
+FRA_DEV int lo16(unsigned w) { return (int)(short)(w & 0xFFFFu); }
+FRA_DEV int hi16(unsigned w) { return ((int)w) >> 16; }
+
+// low 16 bits of two words -> one packed pair (first -> low half)
+FRA_DEV unsigned pack16(unsigned a_bits, unsigned b_bits) { return __byte_perm(a_bits, b_bits, 0x5410); }
+// the same for two offset-binary accumulators -> packed two's-complement int16 pair
+FRA_DEV unsigned pack16_acc(float a, float b)
+{
+    return __byte_perm(__float_as_uint(a), __float_as_uint(b), 0x5410) ^ 0x80008000u;
+}
+
+FRA_DEV uint4 ldg128(const void *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
+FRA_DEV void stg128(void *p, uint4 v) { *reinterpret_cast<uint4 *>(p) = v; }
+
+}  // namespace fra

@@ -1,0 +1,329 @@
+// k2_fft.cuh - K2+K3: batched N-point FFT of real int16 frames with the bin
+// framing fused into the last pass.  One HBM round trip per frame: int16 samples
+// in, 4-byte bins out; everything in between lives in shared memory.
+//
+// Replaces xfft_0 (IP/xfft_0/xfft_0.xci, instance IMP/dsp_system_top.vhd:530-545;
+// input word {im = 0, re = sample}, NEW/command_control.vhd:123), the frame
+// buffer (IMP/sequencer_dsp.vhd:50-82) and the byte order of sequ_2
+// (IMP/sequ2.vhd:153,234), plus the GUI's magnitude decode (GUI:250-260).
+// In bypass mode (0xB1) the window multiply (NEW/hann8192.vhd:36-39) is applied
+// here while loading, so the whole chain is this one kernel.
+//
+// Algorithm (tools/fft_plan_prototype.py is the numpy statement of the same
+// index arithmetic): the real frame is packed as M = N/2 complex points
+// z[m] = x[2m] + i x[2m+1]; z is split into F interleaved sub-sequences of length
+// L (4096 for N >= 8192, else 256); each gets a radix-16 Stockham (autosort)
+// FFT - 3 or 2 passes, butterflies in registers, exchange through one swizzled
+// shared-memory buffer; the last pass does the radix-F combine, the real-input
+// untangle, the Hermitian mirror and the int16 quantise/pack in registers and
+// writes coalesced 4-byte bins.
+#pragma once
+#include "fra_common.cuh"
+
+namespace fra {
+
+struct K2Args {
+    const uint32_t *in;     // [B][N/2] words = int16 pairs
+    const int *rom32;       // window ROM (WIN only)
+    const float2 *tw1;      // [16][16]   W_256^(r k)
+    const float2 *tw2;      // [16][256]  W_4096^(r k)
+    const float2 *twn;      // [N/2]      W_N^e
+    uint32_t *frames;       // [B][N] {re int16, im int16} little-endian, or null
+    float2 *iq;             // [B][N] fp32 bins, or null
+    float *mag;             // [B][N] or null
+    float *phase;           // [B][N] or null
+    float qscale;           // 0.5 * 2^log2_scale (the untangle leaves 2 X[k])
+    int batch;
+};
+
+template <int LOG2N>
+struct FftPlan {
+    static constexpr int N = 1 << LOG2N;
+    static constexpr int M = N / 2;
+    static constexpr int L = (LOG2N >= 13) ? 4096 : 256;
+    static constexpr int F = M / L;
+    static constexpr int NB = L / 16;
+    static constexpr int PASSES = (L == 4096) ? 3 : 2;
+    static constexpr int FPC = (N >= 16384) ? 1 : 16384 / N;   // frames per CTA
+    static constexpr int ITEMS = FPC * F * NB;                  // butterflies per pass per CTA
+    static constexpr int THREADS = ITEMS / 2;                  // two butterflies per thread per pass: 256 (512 at 32K)
+    static constexpr int SMEM_BYTES = FPC * M * 8;
+    static constexpr int SLOTS = FPC * (L / 2);                 // last-pass work items per CTA
+};
+
+FRA_DEV float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+FRA_DEV float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+FRA_DEV float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+FRA_DEV float2 cmulc(float2 a, float2 b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }  // a * conj(b)
+FRA_DEV float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+FRA_DEV float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }     // a * (-i)
+
+// shared-memory index swizzle (complex-element units): makes the stride-16 and
+// stride-256 scatter of the Stockham passes bank-conflict-free for 8-byte accesses
+FRA_DEV int swz(int idx) { return idx ^ ((idx >> 4) & 15); }
+
+FRA_DEV void dft4(float2 &a0, float2 &a1, float2 &a2, float2 &a3)
+{
+    float2 s02 = cadd(a0, a2), d02 = csub(a0, a2), s13 = cadd(a1, a3), d13 = csub(a1, a3);
+    a0 = cadd(s02, s13);
+    a2 = csub(s02, s13);
+    a1 = make_float2(d02.x + d13.y, d02.y - d13.x);
+    a3 = make_float2(d02.x - d13.y, d02.y + d13.x);
+}
+
+// forward 16-point DFT, natural order in and out: r = 4a + b, q = q1 + 4 q2
+FRA_DEV void dft16(const float2 (&v)[16], float2 (&o)[16])
+{
+    const float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, h = 0.70710678118654752f;
+    float2 u[4][4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        u[b][0] = v[b]; u[b][1] = v[4 + b]; u[b][2] = v[8 + b]; u[b][3] = v[12 + b];
+        dft4(u[b][0], u[b][1], u[b][2], u[b][3]);          // u[b][q1]
+    }
+    // twiddle W16^(b q1)
+    u[1][1] = cmul(u[1][1], make_float2(c1, -s1));
+    u[1][2] = make_float2((u[1][2].x + u[1][2].y) * h, (u[1][2].y - u[1][2].x) * h);
+    u[1][3] = cmul(u[1][3], make_float2(s1, -c1));
+    u[2][1] = make_float2((u[2][1].x + u[2][1].y) * h, (u[2][1].y - u[2][1].x) * h);
+    u[2][2] = mul_mi(u[2][2]);
+    u[2][3] = make_float2((u[2][3].y - u[2][3].x) * h, -(u[2][3].x + u[2][3].y) * h);
+    u[3][1] = cmul(u[3][1], make_float2(s1, -c1));
+    u[3][2] = make_float2((u[3][2].y - u[3][2].x) * h, -(u[3][2].x + u[3][2].y) * h);
+    u[3][3] = cmul(u[3][3], make_float2(-c1, s1));
+#pragma unroll
+    for (int q1 = 0; q1 < 4; ++q1) {
+        float2 t0 = u[0][q1], t1 = u[1][q1], t2 = u[2][q1], t3 = u[3][q1];
+        dft4(t0, t1, t2, t3);
+        o[q1] = t0; o[q1 + 4] = t1; o[q1 + 8] = t2; o[q1 + 12] = t3;
+    }
+}
+
+// forward F-point DFT in place, F in {1, 2, 4, 8}
+template <int F>
+FRA_DEV void dft_small(float2 (&a)[F])
+{
+    if (F == 2) {
+        float2 t = a[0];
+        a[0] = cadd(t, a[1]);
+        a[1] = csub(t, a[1]);
+    } else if (F == 4) {
+        dft4(a[0], a[1 % F], a[2 % F], a[3 % F]);
+    } else if (F == 8) {
+        const float h = 0.70710678118654752f;
+        float2 e0 = a[0], e1 = a[2 % F], e2 = a[4 % F], e3 = a[6 % F];
+        float2 o0 = a[1 % F], o1 = a[3 % F], o2 = a[5 % F], o3 = a[7 % F];
+        dft4(e0, e1, e2, e3);
+        dft4(o0, o1, o2, o3);
+        o1 = make_float2((o1.x + o1.y) * h, (o1.y - o1.x) * h);      // W8^1
+        o2 = mul_mi(o2);                                              // W8^2
+        o3 = make_float2((o3.y - o3.x) * h, -(o3.x + o3.y) * h);     // W8^3
+        a[0] = cadd(e0, o0); a[4 % F] = csub(e0, o0);
+        a[1 % F] = cadd(e1, o1); a[5 % F] = csub(e1, o1);
+        a[2 % F] = cadd(e2, o2); a[6 % F] = csub(e2, o2);
+        a[3 % F] = cadd(e3, o3); a[7 % F] = csub(e3, o3);
+    }
+}
+
+// QMODE 0: floor, no saturation (scale <= 1/N cannot overflow); 1: floor + saturate;
+// 2: round-to-nearest-even + saturate.  Returns a float whose bit pattern carries
+// the two's-complement int16 in its low 16 bits (kMagic = 0x4B400000).
+template <int QMODE>
+FRA_DEV float quant(float v, float s)
+{
+    float t = (QMODE == 2) ? __fmaf_rn(v, s, kMagic) : __fmaf_rd(v, s, kMagic);
+    if (QMODE >= 1) t = fminf(fmaxf(t, kMagic - 32768.0f), kMagic + 32767.0f);
+    return t;
+}
+
+struct BinOut {
+    uint32_t *frames;
+    float2 *iq;
+    float *mag;
+    float *phase;
+    float qscale;
+};
+
+// one bin and its conjugate-symmetric partner: X[pos] = p/2, X[pos_conj] = conj(p)/2
+template <int QMODE>
+FRA_DEV void emit_pair(const BinOut &o, size_t frame_base, int pos, int pos_conj, bool write_conj, float2 p)
+{
+    if (o.iq != nullptr) {
+        o.iq[frame_base + pos] = make_float2(0.5f * p.x, 0.5f * p.y);
+        if (write_conj) o.iq[frame_base + pos_conj] = make_float2(0.5f * p.x, -0.5f * p.y);
+    }
+    if (o.frames != nullptr || o.mag != nullptr || o.phase != nullptr) {
+        const float qre = quant<QMODE>(p.x, o.qscale);
+        const float qim = quant<QMODE>(p.y, o.qscale);
+        const float qimc = quant<QMODE>(p.y, -o.qscale);
+        if (o.frames != nullptr) {
+            o.frames[frame_base + pos] = __byte_perm(__float_as_uint(qre), __float_as_uint(qim), 0x5410);
+            if (write_conj)
+                o.frames[frame_base + pos_conj] = __byte_perm(__float_as_uint(qre), __float_as_uint(qimc), 0x5410);
+        }
+        if (o.mag != nullptr || o.phase != nullptr) {
+            const float fre = qre - kMagic, fim = qim - kMagic, fimc = qimc - kMagic;
+            const float re2 = __fmul_rn(fre, fre);
+            if (o.mag != nullptr) {
+                o.mag[frame_base + pos] = __fsqrt_rn(__fadd_rn(re2, __fmul_rn(fim, fim)));
+                if (write_conj) o.mag[frame_base + pos_conj] = __fsqrt_rn(__fadd_rn(re2, __fmul_rn(fimc, fimc)));
+            }
+            if (o.phase != nullptr) {
+                o.phase[frame_base + pos] = atan2f(fim, fre);
+                if (write_conj) o.phase[frame_base + pos_conj] = atan2f(fimc, fre);
+            }
+        }
+    }
+}
+
+// W_16^q, q = 0..7 (the last pass needs W_(2F)^q = W_16^(q * 8 / F))
+FRA_DEV float2 w16(int q)
+{
+    const float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, h = 0.70710678118654752f;
+    switch (q) {
+    case 0: return make_float2(1.0f, 0.0f);
+    case 1: return make_float2(c1, -s1);
+    case 2: return make_float2(h, -h);
+    case 3: return make_float2(s1, -c1);
+    case 4: return make_float2(0.0f, -1.0f);
+    case 5: return make_float2(-s1, -c1);
+    case 6: return make_float2(-h, -h);
+    default: return make_float2(-c1, -s1);
+    }
+}
+
+template <int LOG2N, bool WIN, int QMODE>
+__global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS) k2_fft(K2Args a)
+{
+    using P = FftPlan<LOG2N>;
+    FRA_DYN_SMEM(smem_raw);
+    float2 *buf = reinterpret_cast<float2 *>(smem_raw);
+    const int tid = threadIdx.x;
+    const int frame0 = blockIdx.x * P::FPC;
+
+    // ---------------------------------------------- radix-16 Stockham passes
+#pragma unroll 1
+    for (int pass = 0; pass < P::PASSES; ++pass) {
+        const int ns = (pass == 0) ? 1 : (pass == 1 ? 16 : 256);
+        float2 o[P::ITEMS / P::THREADS][16];
+        int obase[P::ITEMS / P::THREADS];
+#pragma unroll
+        for (int q = 0; q < P::ITEMS / P::THREADS; ++q) {
+            const int it = tid + P::THREADS * q;
+            const int j = it % P::NB;
+            const int f = (it / P::NB) % P::F;
+            const int fr = it / (P::NB * P::F);
+            const int base = fr * P::M + f * P::L;
+            float2 v[16];
+            if (pass == 0) {
+                const int frame = frame0 + fr;
+                const bool live = frame < a.batch;
+                const uint32_t *src = a.in + (size_t)frame * P::M;
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    const int e = P::F * (j + P::NB * r) + f;        // complex index in z
+                    const unsigned w = live ? __ldg(src + e) : 0u;
+                    int x0 = lo16(w), x1 = hi16(w);
+                    if (WIN) {
+                        const int2 c = __ldg(reinterpret_cast<const int2 *>(a.rom32 + ((2 * e) & (kWindowLen - 1))));
+                        x0 = window_int(x0, c.x);
+                        x1 = window_int(x1, c.y);
+                    }
+                    v[r] = make_float2(small_int_to_float(x0), small_int_to_float(x1));
+                }
+            } else {
+                const int k = j % ns;
+                const float2 *tw = (pass == 1) ? (a.tw1 + k) : (a.tw2 + k);
+                const int tws = (pass == 1) ? 16 : 256;
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    float2 x = buf[swz(base + j + P::NB * r)];
+                    if (r > 0) x = cmul(x, __ldg(tw + r * tws));
+                    v[r] = x;
+                }
+            }
+            dft16(v, o[q]);
+            const int k = j % ns;
+            obase[q] = base + (j / ns) * ns * 16 + k;
+        }
+        // pass 0 reads global memory only; the last pass of each size writes back
+        // to the positions it read.  Only the middle pass of L = 4096 scatters into
+        // other threads' read positions and needs the barrier between read and write.
+        if (pass == 1 && P::PASSES == 3) __syncthreads();
+#pragma unroll
+        for (int q = 0; q < P::ITEMS / P::THREADS; ++q) {
+#pragma unroll
+            for (int r = 0; r < 16; ++r) buf[swz(obase[q] + r * ns)] = o[q][r];
+        }
+        __syncthreads();
+    }
+
+    // ---------------- last pass: radix-F combine + untangle + mirror + pack
+    BinOut out;
+    out.frames = a.frames; out.iq = a.iq; out.mag = a.mag; out.phase = a.phase; out.qscale = a.qscale;
+#pragma unroll 1
+    for (int slot = tid; slot < P::SLOTS; slot += P::THREADS) {
+        const int fr = slot / (P::L / 2);
+        const int k0 = slot % (P::L / 2);
+        const int frame = frame0 + fr;
+        if (frame >= a.batch) continue;
+        const size_t fb = (size_t)frame * P::N;
+        const int reps = (k0 == 0) ? 2 : 1;                 // slot 0 also carries the self-paired k = L/2
+#pragma unroll 1
+        for (int rep = 0; rep < reps; ++rep) {
+            const int k = rep ? (P::L / 2) : k0;
+            const int km = (P::L - k) & (P::L - 1);
+            float2 za[P::F], zb[P::F];
+#pragma unroll
+            for (int f = 0; f < P::F; ++f) {
+                const int base = fr * P::M + f * P::L;
+                za[f] = buf[swz(base + k)];
+                zb[f] = buf[swz(base + km)];
+                if (f > 0) {
+                    const float2 w = __ldg(a.twn + 2 * f * k);             // W_M^(f k)
+                    za[f] = cmul(za[f], w);
+                    // W_M^(f (L-k)) = W_F^f * conj(W_M^(f k))
+                    float2 t = cmulc(zb[f], w);
+                    if (P::F == 2) t = make_float2(-t.x, -t.y);                          // W_2^1 = -1
+                    if (P::F == 4) {
+                        if (f == 1) t = mul_mi(t);                                        // -i
+                        if (f == 2) t = make_float2(-t.x, -t.y);
+                        if (f == 3) t = make_float2(-t.y, t.x);                           // +i
+                    }
+                    if (P::F == 8) {
+                        const float h = 0.70710678118654752f;
+                        if (f == 1) t = make_float2((t.x + t.y) * h, (t.y - t.x) * h);
+                        if (f == 2) t = mul_mi(t);
+                        if (f == 3) t = make_float2((t.y - t.x) * h, -(t.x + t.y) * h);
+                        if (f == 4) t = make_float2(-t.x, -t.y);
+                        if (f == 5) t = make_float2(-(t.x + t.y) * h, (t.x - t.y) * h);
+                        if (f == 6) t = make_float2(-t.y, t.x);
+                        if (f == 7) t = make_float2((t.x - t.y) * h, (t.x + t.y) * h);
+                    }
+                    zb[f] = t;
+                }
+            }
+            dft_small<P::F>(za);       // za[q] = Z[k + L q]
+            dft_small<P::F>(zb);       // zb[q] = Z[(L - k) + L q]
+            const float2 wn = __ldg(a.twn + k);                            // W_N^k
+#pragma unroll
+            for (int q = 0; q < P::F; ++q) {
+                const float2 A = za[q];
+                const float2 B = cconj(zb[P::F - 1 - q]);
+                const float2 fe = cadd(A, B);                              // 2 Fe
+                const float2 fo = mul_mi(csub(A, B));                      // 2 Fo
+                // W_N^(k + L q) = W_N^k * W_(2F)^q
+                float2 w = wn;
+                if (q > 0) w = cmul(wn, w16(q * (8 / P::F)));
+                const float2 t = cmul(w, fo);
+                const float2 p = cadd(fe, t);                              // 2 X[j]
+                const float2 m = csub(fe, t);                              // 2 X[M + j]
+                const int j = k + P::L * q;
+                emit_pair<QMODE>(out, fb, j, (P::N - j) & (P::N - 1), j != 0, p);
+                emit_pair<QMODE>(out, fb, (P::M + j) & (P::N - 1), P::M - j, true, m);
+            }
+        }
+    }
+}
+
+}  // namespace fra

@@ -1,0 +1,153 @@
+/* fra.h - C ABI of libfra.so, the B200-native receive chain
+ *   window ROM multiply -> 12th-order IIR (6 int16 x int8 biquads, 2 banks)
+ *   -> N-point FFT -> int16 I/Q bin framing (+ optional fp32 I/Q, magnitude, phase)
+ *
+ * The reference (mfkiwl/fpga-real-time-fft-analyzer) is an FPGA design with a
+ * Python GUI; it has no FFI.  The boundary this library sits behind is the GUI's
+ * receiver-backend contract (scripts/fft_analyzer_gui.py, "GUI" below): 65536-byte
+ * frames out, 1-byte commands (+ 0xF1 and 12 coefficient bytes) in.  Every entry
+ * point cites the reference interface it replaces.  Paths: NEW/ =
+ * SDR_v2.srcs/sources_1/new/, IMP/ = SDR_v2.srcs/sources_1/imports/new/.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 (FRA_OK)
+ * or a negative fra_status; nothing throws; no global mutable state.  A context
+ * is thread-compatible (one thread at a time), matching the GUI's Qt-main-thread
+ * discipline (GUI:1009-1053).  Pointers named d_* are device pointers on the
+ * context's device, h_* are host pointers.  Work is enqueued on the CUDA stream
+ * given to the call (0 = the context's own stream) and is asynchronous unless
+ * stated; launch errors surface from the call that made them or from fra_sync.
+ * There is NO CPU fallback: without a CUDA device fra_create fails with
+ * FRA_ERR_NO_DEVICE.
+ */
+#ifndef FRA_H
+#define FRA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FRA_ABI_VERSION 1
+
+typedef enum fra_status {
+    FRA_OK = 0,
+    FRA_ERR_INVALID = -1,      /* bad argument (null pointer, size, mode byte) */
+    FRA_ERR_NO_DEVICE = -2,    /* no CUDA device / driver */
+    FRA_ERR_CUDA = -3,         /* a CUDA call or kernel failed; see fra_last_cuda_error */
+    FRA_ERR_NOMEM = -4,
+    FRA_ERR_UNSUPPORTED = -5,  /* e.g. fft_size not in 1024..32768 */
+    FRA_ERR_BUSY = -6          /* byte stream ended inside a 0xF1 upload (informational) */
+} fra_status;
+
+/* Command bytes, GUI:28-37; decoded by NEW/command_control.vhd:46-74,
+ * NEW/rx_filter_coeff.vhd:41-66 and IMP/sequ2.vhd:83-96,216. */
+#define FRA_CMD_UART_REQUEST  0xA5
+#define FRA_CMD_RESET         0xFF
+#define FRA_CMD_ETHERNET_MODE 0xEF
+#define FRA_CMD_UART_MODE     0xFE
+#define FRA_CMD_START         0x55
+#define FRA_CMD_FILTER_UPDATE 0xF1
+#define FRA_MODE_BANK0        0x00   /* fixed filter, IMP/filter_iir12.vhd + IMP/filter_pkg.vhd:54-68 */
+#define FRA_MODE_BANK1        0xA1   /* loadable filter, NEW/filter_iir12_cust.vhd */
+#define FRA_MODE_BYPASS       0xB1   /* reset default, NEW/command_control.vhd:31,50 */
+
+#define FRA_WINDOW_LEN   16384       /* NEW/hann.vhd: Hann_ROM(0 to 16383) */
+#define FRA_FRAME_BYTES(n) ((size_t)4 * (size_t)(n))   /* GUI:41-44: 65536 at n = 16384 */
+
+/* fra_create flags */
+#define FRA_ROUND_NEAREST   0x1u     /* int16 bins rounded to nearest-even instead of truncated (floor) */
+#define FRA_K1_FORCE_LANE   0x2u     /* always use the lane-per-channel window+IIR kernel */
+#define FRA_K1_FORCE_SPLIT  0x4u     /* always use the stage-per-lane (systolic) window+IIR kernel */
+
+typedef struct fra_ctx fra_ctx;      /* opaque: ROM, two coefficient banks, IIR state, twiddles, one stream */
+
+/* Lifetime.  n_channels independent channels, fft_size in {1024,...,32768}
+ * (the reference is fixed at 16384: IP/xfft_0/xfft_0.xci:12, IMP/dsp_system_top.vhd:438-449).
+ * After create the control state is the RTL's reset state: mode 0xB1, bank 1 all
+ * zero, IIR history zero, window address 0. */
+int fra_create(fra_ctx **out, int device, int n_channels, int fft_size, unsigned flags);
+int fra_destroy(fra_ctx *ctx);
+
+/* Byte protocol, exactly as it arrives on the reference's UART
+ * (UartReceiver.send_command / send_filter_coefficients, GUI:567-613):
+ * 0x00/0xA1/0xB1 select the stream fed to the FFT; 0xFF = reset; 0xF1 starts a
+ * 12-byte upload into bank 1 during which every byte is data, not a command
+ * (rx_filter_coeff 'busy', NEW/command_control.vhd:51); 0x55/0xA5/0xEF/0xFE are
+ * accepted and recorded (start / frame request / transport) but do not change the
+ * arithmetic.  Takes effect for the next fra_process call; filter history is NOT
+ * cleared by an upload or a mode change.  Returns FRA_ERR_BUSY (not a
+ * failure) if the stream ends inside an upload; the rest may follow in a later call. */
+int fra_command(fra_ctx *ctx, const uint8_t *bytes, size_t n);
+
+/* Same effects without the byte stream. */
+int fra_load_bank1(fra_ctx *ctx, const int8_t coeff[12]);  /* 0xF1 payload: B0,B1,B2,A0,A1,A2 x {set0,set1}, NEW/filter_iir12_cust.vhd:83-94 */
+int fra_set_mode(fra_ctx *ctx, uint8_t mode);              /* 0x00 | 0xA1 | 0xB1, NEW/command_control.vhd:53-58 */
+int fra_reset(fra_ctx *ctx);                               /* 0xFF: history 0, bank 1 = 0, mode 0xB1, window address 0 */
+
+/* Introspection of the control state (what the RTL holds in registers). */
+int fra_get_mode(const fra_ctx *ctx, uint8_t *mode);
+int fra_get_bank(const fra_ctx *ctx, int bank, int8_t coeff[12]);   /* bank 0 = IMP/filter_pkg.vhd constants */
+int fra_get_transport(const fra_ctx *ctx, uint8_t *transport);      /* 0xEF | 0xFE, IMP/sequ2.vhd:83-96 */
+int fra_get_counters(const fra_ctx *ctx, uint64_t *n_start, uint64_t *n_request, uint64_t *n_reset, uint64_t *n_upload);
+int fra_window_rom(int16_t out[FRA_WINDOW_LEN]);                    /* the ROM of NEW/hann.vhd:5-16390 */
+
+/* Optional outputs of one processing step; any pointer may be NULL. */
+typedef struct fra_outputs {
+    int16_t *d_filtered;  /* [C][N] int16: the FFT's input stream (window, then the selected filter) */
+    uint8_t *d_frames;    /* [C][4N] bytes: per bin re_lo,re_hi,im_lo,im_hi (IMP/sequ2.vhd:153,234; GUI:255-257) */
+    float   *d_iq;        /* [C][N][2] fp32 unscaled DFT bins (what np.fft.fft returns) */
+    float   *d_mag;       /* [C][N] fp32 sqrt(re^2+im^2) of the int16 bins, bit-identical to GUI decode_mag_16iq_le (GUI:250-260) */
+    float   *d_phase;     /* [C][N] fp32 atan2(im, re) of the int16 bins (the reference computes no phase) */
+} fra_outputs;
+
+/* One step: every channel's next N samples.
+ *   d_in        [C][N] int16, channel-major (sample n of channel c at c*N + n)
+ *   continuous  != 0: i_valid held high across the frame boundary - IIR history
+ *               carries over from the previous step (NEW/filter_iir_cust.vhd:139-193);
+ *               == 0: a burst after a gap - history starts from zero.
+ *   The window address always restarts at 0 for a frame (N-sample frames aligned to
+ *   the 14-bit address counter, NEW/hann8192.vhd:23,41); for N < 16384 the first N
+ *   ROM entries are used, for N = 32768 the address wraps.
+ * int16 bins = floor(X[k] * 2^log2_scale) (xfft 'scaled' + 'truncation',
+ * IP/xfft_0/xfft_0.xci; default schedule = 1/N), saturated.  Pass
+ * FRA_SCALE_DEFAULT for 1/N. */
+#define FRA_SCALE_DEFAULT 0x7fffffff
+int fra_process(fra_ctx *ctx, const int16_t *d_in, int continuous, int log2_scale,
+                const fra_outputs *out, void *cuda_stream);
+
+/* The same step through host buffers: pinned staging + H2D, fra_process, D2H of
+ * the requested outputs, synchronised on return.  This is the call a GpuReceiver
+ * backend makes per batch of frames; h_out fields are HOST pointers. */
+int fra_process_host(fra_ctx *ctx, const int16_t *h_in, int continuous, int log2_scale,
+                     const fra_outputs *h_out);
+
+/* IIR history, [C][6][4] int16 = per stage (x[n-1], x[n-2], y[n-1], y[n-2])
+ * (registers ve(1..2), vs(1..2) of NEW/filter_iir_cust.vhd:45-46). Device pointers. */
+int fra_get_state(fra_ctx *ctx, int16_t *d_state, void *cuda_stream);
+int fra_set_state(fra_ctx *ctx, const int16_t *d_state, void *cuda_stream);
+
+/* Single long stream (BASELINE config 5): window-free IIR12 of n samples of ONE
+ * channel with the currently selected bank, time-parallel over chunks
+ * (speculative chunked scan: each chunk starts from a state predicted by a
+ * warm-up run, neighbours are verified by warp shuffles, mismatching chunks are
+ * re-run serially - the result is bit-exact).  n_rerun (optional, host) receives the
+ * number of chunks that needed the serial repair.  Synchronous. */
+int fra_iir_stream(fra_ctx *ctx, const int16_t *d_in, int16_t *d_out, size_t n,
+                   int continuous, int *n_rerun);
+
+/* FFT alone (BASELINE config 5 size sweep): batch frames of fft_size int16
+ * samples -> fp32 bins, no window, no filter. */
+int fra_fft_only(fra_ctx *ctx, const int16_t *d_in, int batch, float *d_iq, void *cuda_stream);
+
+int fra_sync(fra_ctx *ctx);                       /* wait for the context's stream */
+int fra_last_kernel_count(const fra_ctx *ctx);    /* kernels launched by the last fra_process */
+const char *fra_last_cuda_error(const fra_ctx *ctx);
+const char *fra_strerror(int status);
+int fra_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FRA_H */

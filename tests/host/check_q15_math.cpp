@@ -1,0 +1,60 @@
+// Exhaustive host check of the FP32-pipe identities the K1 kernels rely on
+// (csrc/fra_common.cuh).  Built and run by tests/test_q15_math_host.py with
+//   g++ -std=c++20 -O1 -frounding-math -DFRA_HOST_EMUL -Itests/emul ...
+// TEST INFRASTRUCTURE ONLY.
+#include "fra_common.cuh"
+#include <cstdio>
+
+static int floordiv128(int p) { return p >> 7; }
+
+int main()
+{
+    using namespace fra;
+    long bad = 0;
+    const float accs[3] = {kMagic, kMagic + 12345.0f, kMagic - 160000.0f};
+    // 1. fma.rm / fma.rp accumulate floor(v*c/128) exactly, for every int16 x int8
+    for (int c = -128; c <= 127; ++c) {
+        float kc = (float)c / 128.0f, nkc = -(float)c / 128.0f;
+        for (int v = -32768; v <= 32767; ++v) {
+            int f = floordiv128(v * c);
+            for (float a0 : accs) {
+                float rd = __fmaf_rd((float)v, kc, a0);
+                float ru = __fmaf_ru((float)v, nkc, a0);
+                if (rd != a0 + (float)f || ru != a0 - (float)f) {
+                    if (bad < 5) std::printf("fma mismatch v=%d c=%d a0=%f rd=%f ru=%f f=%d\n", v, c, a0, rd, ru, f);
+                    ++bad;
+                }
+            }
+        }
+    }
+    // 2. low-16-bit wrap of the magic accumulator -> float, for every reachable sum
+    for (int s = -5 * 32768 - 8; s <= 5 * 32768 + 8; ++s) {
+        float acc = kMagic + (float)s;
+        float y = wrap16_to_float(acc);
+        int want = (int)(short)(unsigned short)(s & 0xFFFF);
+        if (y != (float)want) { if (bad < 10) std::printf("wrap mismatch s=%d y=%f want=%d\n", s, y, want); ++bad; }
+        unsigned bits = __float_as_uint(acc);
+        if ((int)(short)(bits & 0xFFFF) != want) { ++bad; }
+    }
+    // 3. window: every int16 sample x every int16 coefficient vs the VHDL bit recipe
+    for (int c = -32768; c <= 32767; ++c) {
+        for (int x = -32768; x <= 32767; ++x) {
+            int p = x * c;
+            int r17 = (p >> 15) + ((p >> 14) & 1);
+            int sign = (r17 >> 16) & 1;
+            int want = (r17 & 0x7FFF) - (sign << 15);
+            if (window_int(x, c) != want) { if (bad < 15) std::printf("window mismatch x=%d c=%d\n", x, c); ++bad; }
+        }
+    }
+    // 4. small int -> float
+    for (int v = -32768; v <= 32768; ++v)
+        if (small_int_to_float(v) != (float)v) ++bad;
+    // 5. pack16 / lo16 / hi16
+    for (int a = -32768; a <= 32767; a += 257)
+        for (int b = -32768; b <= 32767; b += 263) {
+            unsigned w = pack16(__float_as_uint(kMagic + (float)a), __float_as_uint(kMagic + (float)b));
+            if (lo16(w) != a || hi16(w) != b) ++bad;
+        }
+    std::printf("bad=%ld\n", bad);
+    return bad ? 1 : 0;
+}
