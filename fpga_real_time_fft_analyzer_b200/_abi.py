@@ -38,6 +38,12 @@ class FraOutputs(C.Structure):
                 ("d_mag", C.c_void_p), ("d_phase", C.c_void_p)]
 
 
+class FraStreamStats(C.Structure):
+    """struct fra_stream_stats."""
+    _fields_ = [("exact", C.c_int), ("n_chunks", C.c_int), ("chunk", C.c_int), ("warmup", C.c_int),
+                ("n_mismatch", C.c_int), ("max_state_dev", C.c_int)]
+
+
 # name -> (restype, argtypes); must list every function declared in include/fra.h
 SIGNATURES = {
     "fra_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_uint]),
@@ -55,8 +61,11 @@ SIGNATURES = {
     "fra_process_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(FraOutputs)]),
     "fra_get_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "fra_set_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
-    "fra_iir_stream": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_int)]),
+    "fra_iir_stream": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
+                                 C.POINTER(FraStreamStats)]),
     "fra_fft_only": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "fra_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
+    "fra_profile_last": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "fra_sync": (C.c_int, [C.c_void_p]),
     "fra_last_kernel_count": (C.c_int, [C.c_void_p]),
     "fra_last_cuda_error": (C.c_char_p, [C.c_void_p]),

@@ -10,6 +10,7 @@
 #include "k1b_stream.cuh"
 #include "k2_fft.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -27,6 +28,7 @@ const int16_t kHannRom[kWindowLen] = {
 // IMP/filter_pkg.vhd:54-68 in the register order of NEW/filter_iir12_cust.vhd:83-94
 const int8_t kBank0[12] = {-14, 0, 14, 107, 21, 127, -15, 0, 15, 107, -21, 127};
 
+constexpr int kStreamMaxDeadband = 32;            // LSB; larger boundary differences mean the scan is invalid
 constexpr int kLaneMinChannels = 148 * 4 * 32;   // below this k1_lane cannot fill the SMs' schedulers
 
 }  // namespace
@@ -61,8 +63,12 @@ struct fra_ctx {
     float *d_iq = nullptr, *d_mag = nullptr, *d_phase = nullptr;
     // K1b work space
     int16_t *d_entry = nullptr, *d_exit = nullptr;
-    int *d_flags = nullptr, *d_counts = nullptr;
+    int *d_counts = nullptr;
     int k1b_capacity = 0;
+
+    bool profiling = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // K1 begin/end, K2 begin/end
+    bool ev_k1 = false, ev_k2 = false;
 
     int last_kernels = 0;
     char err[256] = {0};
@@ -172,6 +178,7 @@ int process_range(fra_ctx *ctx, const int16_t *d_in, int c0, int nch, int contin
         k1.channels = nch;
         k1.n = n;
         k1.continuous = continuous;
+        if (ctx->profiling) FRA_TRY(ctx, cudaEventRecord(ctx->ev[0], st));
         bool split = nch < kLaneMinChannels;
         if (ctx->flags & FRA_K1_FORCE_LANE) split = false;
         if (ctx->flags & FRA_K1_FORCE_SPLIT) split = true;
@@ -188,6 +195,10 @@ int process_range(fra_ctx *ctx, const int16_t *d_in, int c0, int nch, int contin
             FRA_LAUNCH(kfn, dim3(grid), dim3(kLaneBlock), (size_t)0, st, k1);
         }
         FRA_TRY(ctx, cudaGetLastError());
+        if (ctx->profiling) {
+            FRA_TRY(ctx, cudaEventRecord(ctx->ev[1], st));
+            ctx->ev_k1 = true;
+        }
         ctx->last_kernels++;
         fft_in = filt;
     } else if (o.d_filtered) {
@@ -214,8 +225,13 @@ int process_range(fra_ctx *ctx, const int16_t *d_in, int c0, int nch, int contin
         k2.batch = nch;
         const bool nearest = (ctx->flags & FRA_ROUND_NEAREST) != 0;
         const int qmode = nearest ? 2 : (log2_scale <= -ctx->log2n ? 0 : 1);
+        if (ctx->profiling) FRA_TRY(ctx, cudaEventRecord(ctx->ev[2], st));
         int rc = launch_k2(ctx, k2, /*win=*/!iir, qmode, st);
         if (rc != FRA_OK) return rc;
+        if (ctx->profiling) {
+            FRA_TRY(ctx, cudaEventRecord(ctx->ev[3], st));
+            ctx->ev_k2 = true;
+        }
     }
     return FRA_OK;
 }
@@ -330,9 +346,11 @@ int fra_destroy(fra_ctx *ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     void *bufs[] = {ctx->d_rom32, ctx->d_state, ctx->d_scratch, ctx->d_tw1, ctx->d_tw2, ctx->d_twn, ctx->d_in,
                     ctx->d_frames, ctx->d_filtered_out, ctx->d_iq, ctx->d_mag, ctx->d_phase, ctx->d_entry,
-                    ctx->d_exit, ctx->d_flags, ctx->d_counts};
+                    ctx->d_exit, ctx->d_counts};
     for (void *p : bufs)
         if (p) cudaFree(p);
+    for (auto e : ctx->ev)
+        if (e) cudaEventDestroy(e);
     for (auto s : ctx->copy_streams)
         if (s) cudaStreamDestroy(s);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -439,12 +457,13 @@ int fra_process(fra_ctx *ctx, const int16_t *d_in, int continuous, int log2_scal
     if (log2_scale == FRA_SCALE_DEFAULT) log2_scale = -ctx->log2n;
     if (log2_scale < -40 || log2_scale > 16) return FRA_ERR_INVALID;
     FRA_TRY(ctx, cudaSetDevice(ctx->device));
-    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    cudaStream_t st = (cudaStream_t)cuda_stream;      // NULL = the legacy default stream
     const bool iir = (ctx->mode == FRA_MODE_BANK0 || ctx->mode == FRA_MODE_BANK1);
     if (iir && !out->d_filtered && !ctx->d_scratch)
         if (cudaMalloc((void **)&ctx->d_scratch, (size_t)ctx->channels * ctx->n * sizeof(int16_t)) != cudaSuccess)
             return FRA_ERR_NOMEM;
     ctx->last_kernels = 0;
+    ctx->ev_k1 = ctx->ev_k2 = false;
     return process_range(ctx, d_in, 0, ctx->channels, continuous, log2_scale, *out, st);
 }
 
@@ -510,7 +529,7 @@ int fra_get_state(fra_ctx *ctx, int16_t *d_state, void *cuda_stream)
 {
     if (!ctx || !d_state) return FRA_ERR_INVALID;
     FRA_TRY(ctx, cudaSetDevice(ctx->device));
-    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    cudaStream_t st = (cudaStream_t)cuda_stream;      // NULL = the legacy default stream
     FRA_TRY(ctx, cudaMemcpyAsync(d_state, ctx->d_state, (size_t)ctx->channels * 24 * sizeof(int16_t),
                                  cudaMemcpyDeviceToDevice, st));
     return FRA_OK;
@@ -520,44 +539,92 @@ int fra_set_state(fra_ctx *ctx, const int16_t *d_state, void *cuda_stream)
 {
     if (!ctx || !d_state) return FRA_ERR_INVALID;
     FRA_TRY(ctx, cudaSetDevice(ctx->device));
-    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    cudaStream_t st = (cudaStream_t)cuda_stream;      // NULL = the legacy default stream
     FRA_TRY(ctx, cudaMemcpyAsync(ctx->d_state, d_state, (size_t)ctx->channels * 24 * sizeof(int16_t),
                                  cudaMemcpyDeviceToDevice, st));
     return FRA_OK;
 }
 
-int fra_iir_stream(fra_ctx *ctx, const int16_t *d_in, int16_t *d_out, size_t n, int continuous, int *n_rerun)
+int fra_iir_stream(fra_ctx *ctx, const int16_t *d_in, int16_t *d_out, size_t n, int continuous, int exact,
+                   fra_stream_stats *stats)
 {
     if (!ctx || !d_in || !d_out || n == 0 || (n % 8) != 0) return FRA_ERR_INVALID;
     FRA_TRY(ctx, cudaSetDevice(ctx->device));
-    const int chunk = 4096, warm = 2048;
+    cudaStream_t st = ctx->stream;
+    const bool iir = (ctx->mode == FRA_MODE_BANK0 || ctx->mode == FRA_MODE_BANK1);
+    const int8_t *bank = (ctx->mode == FRA_MODE_BANK1) ? ctx->bank1 : kBank0;
+    fra_stream_stats s = {0, 0, 0, 0, 0, 0};
+
+    // warm-up length from the pole radius of z^2 + (A1/128) z + A0/128 (both sets)
+    int warm = 0;
+    if (iir && !exact) {
+        double r = 0.0;
+        for (int set = 0; set < 2; ++set) {
+            const double a0 = bank[6 * set + 3] / 128.0, a1 = bank[6 * set + 4] / 128.0;
+            const double disc = a1 * a1 - 4.0 * a0;
+            const double rs = disc < 0.0 ? std::sqrt(a0)
+                                         : std::max(std::fabs((-a1 + std::sqrt(disc)) / 2.0), std::fabs((-a1 - std::sqrt(disc)) / 2.0));
+            r = std::max(r, rs);
+        }
+        if (r >= 0.9995) exact = 1;                       // no bounded warm-up: use the exact chain
+        else if (r > 0.0) warm = (int)std::ceil(18.0 * 0.6931471805599453 / -std::log(r));
+        warm = std::max(256, ((warm + 7) / 8) * 8) * 6;   // six cascaded sections settle one after another
+    }
+
+    ctx->last_kernels = 0;
+    // bit-exact path: the six stages as a systolic chain on six lanes of one warp
+    auto run_exact = [&]() -> int {
+        if ((n % kSplitChunk) != 0 || n > 0x7fffff00u) return FRA_ERR_INVALID;
+        K1Args k1;
+        k1.in = d_in;
+        k1.out = d_out;
+        k1.state = ctx->d_state;
+        k1.rom32 = ctx->d_rom32;
+        k1.coef = make_cascade(bank);
+        k1.channels = 1;
+        k1.n = (int)n;
+        k1.continuous = continuous;
+        const size_t smem = (size_t)kSplitWarps * kSplitSmemPerWarp;
+        auto kfn = k1_split;
+        FRA_TRY(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FRA_LAUNCH(kfn, dim3(1), dim3(kSplitWarps * 32), smem, st, k1);
+        FRA_TRY(ctx, cudaGetLastError());
+        ctx->last_kernels++;
+        FRA_TRY(ctx, cudaStreamSynchronize(st));
+        s.exact = 1;
+        return FRA_OK;
+    };
+    if (exact && iir) {
+        int rc = run_exact();
+        s.n_chunks = 1;
+        s.chunk = (int)n;
+        if (stats) *stats = s;
+        return rc;
+    }
+
+    const int chunk = std::max(4096, 8 * warm);
     const int n_chunks = (int)((n + chunk - 1) / chunk);
     if (n_chunks > ctx->k1b_capacity) {
-        void *old[] = {ctx->d_entry, ctx->d_exit, ctx->d_flags};
+        void *old[] = {ctx->d_entry, ctx->d_exit};
         for (void *p : old)
             if (p) cudaFree(p);
         ctx->d_entry = ctx->d_exit = nullptr;
-        ctx->d_flags = nullptr;
         ctx->k1b_capacity = 0;
         if (cudaMalloc((void **)&ctx->d_entry, (size_t)n_chunks * 24 * sizeof(int16_t)) != cudaSuccess ||
-            cudaMalloc((void **)&ctx->d_exit, (size_t)n_chunks * 24 * sizeof(int16_t)) != cudaSuccess ||
-            cudaMalloc((void **)&ctx->d_flags, (size_t)n_chunks * sizeof(int)) != cudaSuccess)
+            cudaMalloc((void **)&ctx->d_exit, (size_t)n_chunks * 24 * sizeof(int16_t)) != cudaSuccess)
             return FRA_ERR_NOMEM;
         ctx->k1b_capacity = n_chunks;
     }
     if (!ctx->d_counts && cudaMalloc((void **)&ctx->d_counts, 2 * sizeof(int)) != cudaSuccess) return FRA_ERR_NOMEM;
-    cudaStream_t st = ctx->stream;
-    const bool iir = (ctx->mode == FRA_MODE_BANK0 || ctx->mode == FRA_MODE_BANK1);
     K1bArgs a;
     a.in = d_in;
     a.out = d_out;
     a.rom32 = ctx->d_rom32;
-    a.coef = make_cascade(ctx->mode == FRA_MODE_BANK1 ? ctx->bank1 : kBank0);
+    a.coef = make_cascade(bank);
     a.entry = ctx->d_entry;
     a.exit_ = ctx->d_exit;
     a.state0 = ctx->d_state;
-    a.flags = ctx->d_flags;
-    a.n_bad = ctx->d_counts;
+    a.stats = ctx->d_counts;
     a.n = n;
     a.chunk = chunk;
     a.warm = warm;
@@ -565,41 +632,42 @@ int fra_iir_stream(fra_ctx *ctx, const int16_t *d_in, int16_t *d_out, size_t n, 
     a.continuous = continuous;
     a.apply_window = 1;
     a.iir = iir ? 1 : 0;
-    ctx->last_kernels = 0;
     FRA_TRY(ctx, cudaMemsetAsync(ctx->d_counts, 0, 2 * sizeof(int), st));
-    {
-        auto kfn = k1b_speculate;
-        FRA_LAUNCH(kfn, dim3((n_chunks + 63) / 64), dim3(64), (size_t)0, st, a);
-        FRA_TRY(ctx, cudaGetLastError());
-        auto vfn = k1b_verify;
-        FRA_LAUNCH(vfn, dim3((n_chunks + 127) / 128), dim3(128), (size_t)0, st, a);
-        FRA_TRY(ctx, cudaGetLastError());
-        ctx->last_kernels += 2;
-    }
+    auto kfn = k1b_speculate;
+    FRA_LAUNCH(kfn, dim3((n_chunks + 63) / 64), dim3(64), (size_t)0, st, a);
+    FRA_TRY(ctx, cudaGetLastError());
+    auto vfn = k1b_verify;
+    FRA_LAUNCH(vfn, dim3((n_chunks + 127) / 128), dim3(128), (size_t)0, st, a);
+    FRA_TRY(ctx, cudaGetLastError());
+    ctx->last_kernels += 2;
     int counts[2] = {0, 0};
     FRA_TRY(ctx, cudaMemcpyAsync(counts, ctx->d_counts, sizeof(counts), cudaMemcpyDeviceToHost, st));
     FRA_TRY(ctx, cudaStreamSynchronize(st));
-    if (counts[0] > 0) {
-        auto rfn = k1b_repair;
-        FRA_LAUNCH(rfn, dim3(1), dim3(32), (size_t)0, st, a, ctx->d_counts + 1);
-        FRA_TRY(ctx, cudaGetLastError());
-        ctx->last_kernels++;
-        FRA_TRY(ctx, cudaMemcpyAsync(counts, ctx->d_counts, sizeof(counts), cudaMemcpyDeviceToHost, st));
+    s.n_chunks = n_chunks;
+    s.chunk = chunk;
+    s.warmup = warm;
+    s.n_mismatch = counts[0];
+    s.max_state_dev = counts[1];
+    int rc = FRA_OK;
+    if (iir && counts[1] > kStreamMaxDeadband && (n % kSplitChunk) == 0) {
+        // beyond the dead band: the cascade is overflowing (16-bit wrap) or barely
+        // stable, trajectories do not stay together - recompute exactly
+        rc = run_exact();
+    } else if (iir) {
+        // the stream's end state becomes channel 0's history (continuous operation)
+        FRA_TRY(ctx, cudaMemcpyAsync(ctx->d_state, ctx->d_exit + (size_t)(n_chunks - 1) * 24, 24 * sizeof(int16_t),
+                                     cudaMemcpyDeviceToDevice, st));
         FRA_TRY(ctx, cudaStreamSynchronize(st));
     }
-    // the stream's end state becomes channel 0's history (continuous operation)
-    FRA_TRY(ctx, cudaMemcpyAsync(ctx->d_state, ctx->d_exit + (size_t)(n_chunks - 1) * 24, 24 * sizeof(int16_t),
-                                 cudaMemcpyDeviceToDevice, st));
-    FRA_TRY(ctx, cudaStreamSynchronize(st));
-    if (n_rerun) *n_rerun = counts[1];
-    return FRA_OK;
+    if (stats) *stats = s;
+    return rc;
 }
 
 int fra_fft_only(fra_ctx *ctx, const int16_t *d_in, int batch, float *d_iq, void *cuda_stream)
 {
     if (!ctx || !d_in || !d_iq || batch <= 0) return FRA_ERR_INVALID;
     FRA_TRY(ctx, cudaSetDevice(ctx->device));
-    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    cudaStream_t st = (cudaStream_t)cuda_stream;      // NULL = the legacy default stream
     K2Args k2;
     k2.in = reinterpret_cast<const uint32_t *>(d_in);
     k2.rom32 = ctx->d_rom32;
@@ -614,6 +682,36 @@ int fra_fft_only(fra_ctx *ctx, const int16_t *d_in, int batch, float *d_iq, void
     k2.batch = batch;
     ctx->last_kernels = 0;
     return launch_k2(ctx, k2, /*win=*/false, /*qmode=*/0, st);
+}
+
+int fra_profile_enable(fra_ctx *ctx, int on)
+{
+    if (!ctx) return FRA_ERR_INVALID;
+    FRA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (on)
+        for (auto &e : ctx->ev)
+            if (!e) FRA_TRY(ctx, cudaEventCreateWithFlags(&e, 0));
+    ctx->profiling = on != 0;
+    ctx->ev_k1 = ctx->ev_k2 = false;
+    return FRA_OK;
+}
+
+int fra_profile_last(fra_ctx *ctx, float *ms_window_iir, float *ms_fft_pack)
+{
+    if (!ctx || !ctx->profiling) return FRA_ERR_INVALID;
+    FRA_TRY(ctx, cudaSetDevice(ctx->device));
+    float a = 0.0f, b = 0.0f;
+    if (ctx->ev_k1) {
+        FRA_TRY(ctx, cudaEventSynchronize(ctx->ev[1]));
+        FRA_TRY(ctx, cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]));
+    }
+    if (ctx->ev_k2) {
+        FRA_TRY(ctx, cudaEventSynchronize(ctx->ev[3]));
+        FRA_TRY(ctx, cudaEventElapsedTime(&b, ctx->ev[2], ctx->ev[3]));
+    }
+    if (ms_window_iir) *ms_window_iir = a;
+    if (ms_fft_pack) *ms_fft_pack = b;
+    return FRA_OK;
 }
 
 int fra_sync(fra_ctx *ctx)

@@ -1,18 +1,22 @@
 // k1b_stream.cuh - K1b: window + IIR12 of ONE long stream, parallel in time.
 //
 // The biquad of NEW/filter_iir_cust.vhd:96-100 truncates every product, so the
-// recurrence is not linear and a plain linear-recurrence scan cannot reproduce
-// it bit for bit.  K1b is a speculative chunked scan that stays exact:
+// recurrence is not linear: trajectories started from different histories do not
+// merge, they settle a few LSB apart (the dead band of a truncating second-order
+// section, the same mechanism as its zero-input limit cycles).  A time-parallel
+// evaluation therefore cannot be bit-exact; K1b is the chunked scan with that
+// stated error, and the bit-exact answer for one stream is the systolic k1_split
+// kernel with one channel (fra_iir_stream(exact = 1)).
 //   1. speculate  one lane per chunk: start `warm` samples before the chunk from
-//                 a zero history, run the exact cascade up to the chunk start
-//                 (the filter forgets its start state as its poles decay), record
-//                 the entry state, filter the chunk, record the exit state;
+//                 a zero history and run the exact cascade up to the chunk start.
+//                 The linear part of the missing history is A^warm * s, below half
+//                 an LSB once warm >= 18 ln2 / -ln(pole radius): the block scan of
+//                 the state-space recurrence truncated to its nearest neighbour,
+//                 which is all that survives for a stable cascade.  Then filter
+//                 the chunk; record entry and exit states;
 //   2. verify     neighbouring chunks compare exit(p-1) with entry(p) - the
-//                 neighbour's state travels by warp shuffle - and flag mismatches;
-//   3. repair     flagged chunks are re-run serially from the true exit state,
-//                 propagating until the states agree again.
-// If every entry state equals its neighbour's exit state the output equals the
-// serial filter's by induction from chunk 0, which starts from the true state.
+//                 neighbour's state travels one lane up by warp shuffle - and
+//                 report how many differ and by how many LSB at most.
 #pragma once
 #include "fra_common.cuh"
 
@@ -26,8 +30,7 @@ struct K1bArgs {
     int16_t *entry;         // [P][24] state at each chunk's first sample
     int16_t *exit_;         // [P][24] state after each chunk's last sample
     const int16_t *state0;  // [24] true state before sample 0 (used when continuous)
-    int *flags;             // [P] mismatch flags; flags[0] unused
-    int *n_bad;             // number of mismatching chunks
+    int *stats;             // [0] chunks whose entry state differs from the neighbour's exit, [1] max |difference| (LSB)
     unsigned long long n;   // samples
     int chunk;              // samples per chunk (multiple of 8)
     int warm;               // warm-up samples
@@ -114,6 +117,12 @@ __global__ void __launch_bounds__(64) k1b_speculate(K1bArgs a)
 
 // verify: lane p compares its entry state with lane p-1's exit state; the exit
 // state moves one lane up by shuffle (the warp's first lane reads it from memory)
+FRA_DEV int absdiff16(unsigned a, unsigned b)
+{
+    const int d0 = lo16(a) - lo16(b), d1 = hi16(a) - hi16(b);
+    return max(d0 < 0 ? -d0 : d0, d1 < 0 ? -d1 : d1);
+}
+
 __global__ void __launch_bounds__(128) k1b_verify(K1bArgs a)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -122,7 +131,7 @@ __global__ void __launch_bounds__(128) k1b_verify(K1bArgs a)
     const int pc = live ? p : a.n_chunks - 1;
     const uint2 *ex = reinterpret_cast<const uint2 *>(a.exit_ + (size_t)pc * 24);
     const uint2 *en = reinterpret_cast<const uint2 *>(a.entry + (size_t)pc * 24);
-    int diff = 0;
+    int dev = 0;
 #pragma unroll
     for (int s = 0; s < kStages; ++s) {
         const uint2 mine = ex[s];
@@ -133,38 +142,12 @@ __global__ void __launch_bounds__(128) k1b_verify(K1bArgs a)
             px = prev.x; py = prev.y;
         }
         const uint2 e = en[s];
-        diff |= (int)((e.x ^ px) | (e.y ^ py));
+        dev = max(dev, max(absdiff16(e.x, px), absdiff16(e.y, py)));
     }
-    if (live && p > 0) {
-        const int bad = diff != 0;
-        a.flags[p] = bad;
-        if (bad) atomicAdd(a.n_bad, 1);
+    if (live && p > 0 && dev != 0) {
+        atomicAdd(a.stats, 1);
+        atomicMax(a.stats + 1, dev);
     }
-}
-
-// repair: serial walk; a chunk is re-run when its entry state is not the true
-// exit state of its predecessor (which may itself just have been repaired)
-__global__ void __launch_bounds__(32) k1b_repair(K1bArgs a, int *n_rerun)
-{
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    int reruns = 0;
-    for (int p = 1; p < a.n_chunks; ++p) {
-        const int16_t *prev = a.exit_ + (size_t)(p - 1) * 24;
-        int16_t *en = a.entry + (size_t)p * 24;
-        bool same = true;
-        for (int i = 0; i < 24; ++i) same = same && (prev[i] == en[i]);
-        if (same) continue;
-        StageState st[kStages];
-        state_load(st, prev);
-        for (int i = 0; i < 24; ++i) en[i] = prev[i];
-        const unsigned long long start = (unsigned long long)p * (unsigned long long)a.chunk;
-        unsigned long long end = start + (unsigned long long)a.chunk;
-        if (end > a.n) end = a.n;
-        stream_run<true>(a, st, start, end);
-        state_store(st, a.exit_ + (size_t)p * 24);
-        ++reruns;
-    }
-    *n_rerun = reruns;
 }
 
 }  // namespace fra

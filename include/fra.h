@@ -13,9 +13,11 @@
  * or a negative fra_status; nothing throws; no global mutable state.  A context
  * is thread-compatible (one thread at a time), matching the GUI's Qt-main-thread
  * discipline (GUI:1009-1053).  Pointers named d_* are device pointers on the
- * context's device, h_* are host pointers.  Work is enqueued on the CUDA stream
- * given to the call (0 = the context's own stream) and is asynchronous unless
- * stated; launch errors surface from the call that made them or from fra_sync.
+ * context's device, h_* are host pointers.  Calls that take a `cuda_stream` enqueue
+ * on exactly that stream (a cudaStream_t; NULL = the CUDA legacy default stream) and
+ * return without waiting; the caller orders them against its own work as with any
+ * CUDA library.  Calls without a stream argument are synchronous.  Launch errors
+ * surface from the call that made them.
  * There is NO CPU fallback: without a CUDA device fra_create fails with
  * FRA_ERR_NO_DEVICE.
  */
@@ -128,18 +130,42 @@ int fra_process_host(fra_ctx *ctx, const int16_t *h_in, int continuous, int log2
 int fra_get_state(fra_ctx *ctx, int16_t *d_state, void *cuda_stream);
 int fra_set_state(fra_ctx *ctx, const int16_t *d_state, void *cuda_stream);
 
-/* Single long stream (BASELINE config 5): window-free IIR12 of n samples of ONE
- * channel with the currently selected bank, time-parallel over chunks
- * (speculative chunked scan: each chunk starts from a state predicted by a
- * warm-up run, neighbours are verified by warp shuffles, mismatching chunks are
- * re-run serially - the result is bit-exact).  n_rerun (optional, host) receives the
- * number of chunks that needed the serial repair.  Synchronous. */
+/* Single long stream (BASELINE config 5): window + IIR12 of n samples of ONE
+ * channel (channel 0's history; window address free-running from 0) with the
+ * currently selected mode.
+ *   exact != 0  bit-exact: the six stages run as a systolic chain on six warp lanes
+ *               (the stage-per-lane kernel with one channel); n must be a multiple of 256.
+ *   exact == 0  time-parallel chunked scan: one lane per chunk, each chunk's entry
+ *               state predicted by a warm-up run whose length is set from the pole
+ *               radius, neighbours verified by warp shuffles.  Because every product
+ *               is truncated (NEW/filter_iir_cust.vhd:96-100) the cascade is not linear
+ *               and this path is NOT bit-exact: it settles within the dead band of the
+ *               truncating sections, a few LSB from the serial result; `stats` reports
+ *               how many chunk boundaries differ and by how many LSB.  n multiple of 8.
+ *               Falls back to the exact path when the poles are too close to the unit
+ *               circle for a bounded warm-up (stats->exact is set).
+ * Synchronous. */
+typedef struct fra_stream_stats {
+    int exact;          /* 1 if the exact path produced the output */
+    int n_chunks;
+    int chunk;          /* samples per chunk */
+    int warmup;         /* warm-up samples per chunk */
+    int n_mismatch;     /* chunk boundaries whose predicted entry state != neighbour's exit state */
+    int max_state_dev;  /* largest such difference, LSB */
+} fra_stream_stats;
 int fra_iir_stream(fra_ctx *ctx, const int16_t *d_in, int16_t *d_out, size_t n,
-                   int continuous, int *n_rerun);
+                   int continuous, int exact, fra_stream_stats *stats);
 
 /* FFT alone (BASELINE config 5 size sweep): batch frames of fft_size int16
  * samples -> fp32 bins, no window, no filter. */
 int fra_fft_only(fra_ctx *ctx, const int16_t *d_in, int batch, float *d_iq, void *cuda_stream);
+
+/* Per-kernel device timing of fra_process (bench.py's roofline): when enabled,
+ * CUDA events are recorded on the launching stream around the window+IIR kernel
+ * and around the FFT+pack kernel.  fra_profile_last waits for the last step and
+ * returns the two durations in milliseconds (0 for a kernel that did not run). */
+int fra_profile_enable(fra_ctx *ctx, int on);
+int fra_profile_last(fra_ctx *ctx, float *ms_window_iir, float *ms_fft_pack);
 
 int fra_sync(fra_ctx *ctx);                       /* wait for the context's stream */
 int fra_last_kernel_count(const fra_ctx *ctx);    /* kernels launched by the last fra_process */

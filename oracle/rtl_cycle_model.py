@@ -12,7 +12,7 @@ from __future__ import annotations
 
 def _s(v: int, bits: int) -> int:
     """Interpret the low ``bits`` bits of v as two's complement."""
-    v &= (1 << bits) - 1
+    v = int(v) & ((1 << bits) - 1)
     return v - (1 << bits) if v >> (bits - 1) else v
 
 

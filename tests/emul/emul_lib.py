@@ -96,13 +96,14 @@ class EmulFra:
         st = np.ascontiguousarray(st, dtype=np.int16)
         assert self.L.fra_set_state(self.h, st.ctypes.data, None) == 0
 
-    def iir_stream(self, x, continuous=False):
+    def iir_stream(self, x, continuous=False, exact=False):
         x = np.ascontiguousarray(x, dtype=np.int16)
         y = np.zeros_like(x)
-        nr = C.c_int(-1)
-        rc = self.L.fra_iir_stream(self.h, x.ctypes.data, y.ctypes.data, x.size, int(continuous), C.byref(nr))
+        st = _abi.FraStreamStats()
+        rc = self.L.fra_iir_stream(self.h, x.ctypes.data, y.ctypes.data, x.size, int(continuous), int(exact),
+                                   C.byref(st))
         assert rc == 0, rc
-        return y, nr.value
+        return y, {k: getattr(st, k) for k, _ in st._fields_}
 
     def fft_only(self, x):
         x = np.ascontiguousarray(x, dtype=np.int16).reshape(-1, self.n)

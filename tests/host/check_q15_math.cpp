@@ -4,6 +4,7 @@
 // TEST INFRASTRUCTURE ONLY.
 #include "fra_common.cuh"
 #include <cstdio>
+// a full biquad step against the integer recipe is covered by tests/test_emul_kernels.py
 
 static int floordiv128(int p) { return p >> 7; }
 
@@ -11,7 +12,7 @@ int main()
 {
     using namespace fra;
     long bad = 0;
-    const float accs[3] = {kMagic, kMagic + 12345.0f, kMagic - 160000.0f};
+    const float accs[3] = {kMagicB, kMagicB + 131072.0f, kMagicB - 131072.0f};
     // 1. fma.rm / fma.rp accumulate floor(v*c/128) exactly, for every int16 x int8
     for (int c = -128; c <= 127; ++c) {
         float kc = (float)c / 128.0f, nkc = -(float)c / 128.0f;
@@ -27,14 +28,13 @@ int main()
             }
         }
     }
-    // 2. low-16-bit wrap of the magic accumulator -> float, for every reachable sum
+    // 2. low-16-bit wrap of the offset-binary accumulator -> float, for every reachable sum
     for (int s = -5 * 32768 - 8; s <= 5 * 32768 + 8; ++s) {
-        float acc = kMagic + (float)s;
+        float acc = kMagicB + (float)s;
         float y = wrap16_to_float(acc);
         int want = (int)(short)(unsigned short)(s & 0xFFFF);
         if (y != (float)want) { if (bad < 10) std::printf("wrap mismatch s=%d y=%f want=%d\n", s, y, want); ++bad; }
-        unsigned bits = __float_as_uint(acc);
-        if ((int)(short)(bits & 0xFFFF) != want) { ++bad; }
+        if ((int)(short)acc_to_u16(acc) != want) { ++bad; }
     }
     // 3. window: every int16 sample x every int16 coefficient vs the VHDL bit recipe
     for (int c = -32768; c <= 32767; ++c) {
@@ -54,6 +54,8 @@ int main()
         for (int b = -32768; b <= 32767; b += 263) {
             unsigned w = pack16(__float_as_uint(kMagic + (float)a), __float_as_uint(kMagic + (float)b));
             if (lo16(w) != a || hi16(w) != b) ++bad;
+            unsigned w2 = pack16_acc(kMagicB + (float)a, kMagicB + (float)b);
+            if (lo16(w2) != a || hi16(w2) != b) ++bad;
         }
     std::printf("bad=%ld\n", bad);
     return bad ? 1 : 0;

@@ -1,0 +1,260 @@
+"""Parity of the CUDA path (through the C ABI, via FraContext) with the oracle on a
+real B200.  Bars: window + IIR12 bit-exact; fp32 bins within 1e-4 relative L2 of a
+numpy float64 FFT of the same filtered frames (BASELINE.json north_star); int16 bins
+= floor(own fp32 bins * scale) exactly and within 1 LSB of the float64 oracle;
+magnitude bit-identical to the GUI decode of the same frame."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from oracle import cgolden as cg          # noqa: E402  (checker only)
+from oracle import golden as g            # noqa: E402
+
+B1 = np.array([32, 10, -33, 119, 35, 0, 52, -16, 11, 84, -10, 0], dtype=np.int8)
+FFT_TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def fra():
+    if not torch.cuda.is_available():
+        pytest.fail("-m gpu tests need a CUDA device; there is no CPU fallback")
+    import fpga_real_time_fft_analyzer_b200 as pkg
+    from fpga_real_time_fft_analyzer_b200 import _abi, synth
+    pkg._abi = _abi
+    pkg.synth = synth
+    return pkg
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def adversarial(rng, c, n):
+    x = rng.integers(-32768, 32768, size=(c, n)).astype(np.int16)
+    x[0, :40] = -32768
+    x[-1, -40:] = -32768
+    return x
+
+
+def rel_l2(got, ref):
+    return float(np.linalg.norm(got - ref) / np.linalg.norm(ref))
+
+
+@pytest.mark.parametrize("variant", ["lane", "split"])
+@pytest.mark.parametrize("channels", [1, 5, 33, 257])
+def test_k1_bit_exact_state_reload(fra, rom, variant, channels):
+    flags = fra._abi.FRA_K1_FORCE_LANE if variant == "lane" else fra._abi.FRA_K1_FORCE_SPLIT
+    rng = np.random.default_rng(channels)
+    n = 16384
+    with fra.FraContext(channels, n, flags=flags) as ctx:
+        ctx.command(0x00)
+        st = None
+        for frame in range(3):                       # state carried over >= 3 frames
+            x = adversarial(rng, channels, n)
+            y, st = cg.window_iir(x, rom, 0x00, g.BANK0_COEFF, B1, st)
+            out = ctx.process(dev(x), continuous=frame > 0, want=("filtered",))
+            assert np.array_equal(out["filtered"].cpu().numpy(), y), (variant, channels, frame)
+            assert np.array_equal(ctx.get_state().cpu().numpy(), st)
+        # mid-stream 0xF1 reload + bank switch at a frame boundary, history retained
+        assert ctx.command(bytes([0xF1]) + B1.tobytes()) and ctx.command(0xA1)
+        x = adversarial(rng, channels, n)
+        y, st = cg.window_iir(x, rom, 0xA1, g.BANK0_COEFF, B1, st)
+        out = ctx.process(dev(x), continuous=True, want=("filtered",))
+        assert np.array_equal(out["filtered"].cpu().numpy(), y)
+        # burst after a gap: history from zero
+        y, st = cg.window_iir(x, rom, 0xA1, g.BANK0_COEFF, B1, None)
+        out = ctx.process(dev(x), continuous=False, want=("filtered",))
+        assert np.array_equal(out["filtered"].cpu().numpy(), y)
+        assert np.array_equal(ctx.get_state().cpu().numpy(), st)
+
+
+@pytest.mark.parametrize("seed", range(1, 9))
+def test_k1_random_int8_coefficients_fuzz(fra, rom, seed):
+    rng = np.random.default_rng(seed)
+    n, c = 2048, 70
+    coef = rng.integers(-128, 128, 12).astype(np.int8)
+    if seed == 1:
+        coef[:] = [-128, 127, -128, -128, 127, 0, 127, -128, 127, 127, -128, 0]
+    for flags in (fra._abi.FRA_K1_FORCE_LANE, fra._abi.FRA_K1_FORCE_SPLIT):
+        with fra.FraContext(c, n, flags=flags) as ctx:
+            ctx.load_bank1(coef)
+            ctx.set_mode(0xA1)
+            st0 = rng.integers(-32768, 32768, (c, 6, 4)).astype(np.int16)
+            ctx.set_state(dev(st0))
+            x = adversarial(rng, c, n)
+            y, st = cg.window_iir(x, rom, 0xA1, g.BANK0_COEFF, coef, st0)
+            out = ctx.process(dev(x), continuous=True, want=("filtered",))
+            assert np.array_equal(out["filtered"].cpu().numpy(), y)
+            assert np.array_equal(ctx.get_state().cpu().numpy(), st)
+
+
+@pytest.mark.parametrize("n", [1024, 2048, 4096, 8192, 16384, 32768])
+def test_fft_sizes_tolerance_and_framing(fra, rom, n):
+    rng = np.random.default_rng(n)
+    b = 3 * max(1, 16384 // n) + 1
+    x = adversarial(rng, b, n)
+    log2n = int(np.log2(n))
+    with fra.FraContext(b, n) as ctx:
+        got = ctx.fft_only(dev(x)).cpu().numpy()
+        ref = np.fft.fft(x.astype(np.float64), axis=-1)
+        assert rel_l2(got, ref) < FFT_TOL
+        assert max(rel_l2(got[i], ref[i]) for i in range(b)) < FFT_TOL          # per frame, too
+        out = ctx.process(dev(x), want=("filtered", "frames", "iq", "mag", "phase"))     # bypass: window fused
+        out = {k: v.cpu().numpy() for k, v in out.items()}
+        w = g.window(x, rom)
+        assert np.array_equal(out["filtered"], w)
+        ref = np.fft.fft(w.astype(np.float64), axis=-1)
+        got = out["iq"][..., 0] + 1j * out["iq"][..., 1]
+        assert rel_l2(got, ref) < FFT_TOL
+        assert np.array_equal(cg.quantize_pack(got.astype(np.complex128), -log2n, 0), out["frames"])
+        re, im, mag = g.decode_frame(out["frames"])
+        rq, iq_ = g.quantize_bins(ref, -log2n)
+        assert np.abs(re - rq).max() <= 1 and np.abs(im - iq_).max() <= 1
+        assert ((re != rq) | (im != iq_)).mean() < 1e-3
+        assert np.array_equal(mag.view(np.uint32), out["mag"].view(np.uint32))
+        assert np.abs(out["phase"] - np.arctan2(im, re)).max() < 2e-6
+
+
+def test_full_chain_tone_noise_and_host_path(fra, rom):
+    n, c = 16384, 96
+    x = g.tone_noise(range(c), n=n, seed=4)
+    with fra.FraContext(c, n) as ctx:
+        ctx.command(0x00)
+        a = {k: v.cpu().numpy() for k, v in ctx.process(dev(x), want=("filtered", "frames", "iq", "mag")).items()}
+        pinned = torch.from_numpy(x).pin_memory()
+        b = {k: v.numpy().copy() for k, v in ctx.process_host(pinned, want=("filtered", "frames", "iq", "mag")).items()}
+        for k in a:
+            assert np.array_equal(a[k], b[k]), k
+        y, _ = cg.window_iir(x, rom, 0, g.BANK0_COEFF, B1)
+        assert np.array_equal(a["filtered"], y)
+        ref = np.fft.fft(y.astype(np.float64), axis=-1)
+        got = a["iq"][..., 0] + 1j * a["iq"][..., 1]
+        assert rel_l2(got, ref) < FFT_TOL
+        # the tone of channel c sits at bin round(f_c / fs * N) of the filtered spectrum's peak neighbourhood
+        _, _, mag = g.decode_frame(a["frames"])
+        assert np.array_equal(mag.view(np.uint32), a["mag"].view(np.uint32))
+
+
+def test_scale_rounding_saturation(fra, rom):
+    n, c = 4096, 5
+    x = adversarial(np.random.default_rng(5), c, n)
+    for flags, rounding in ((0, 0), (fra._abi.FRA_ROUND_NEAREST, 1)):
+        with fra.FraContext(c, n, flags=flags) as ctx:
+            for ls in (-12, -8, 0):
+                out = ctx.process(dev(x), log2_scale=ls, want=("frames", "iq"))
+                iq = out["iq"].cpu().numpy()
+                got = (iq[..., 0] + 1j * iq[..., 1]).astype(np.complex128)
+                assert np.array_equal(cg.quantize_pack(got, ls, rounding), out["frames"].cpu().numpy()), (flags, ls)
+
+
+def test_reset_semantics(fra, rom):
+    n, c = 2048, 12
+    x = adversarial(np.random.default_rng(2), c, n)
+    with fra.FraContext(c, n) as ctx:
+        ctx.command(bytes([0xF1]) + B1.tobytes() + bytes([0xA1]))
+        ctx.process(dev(x), want=("filtered",))
+        assert ctx.get_state().any().item()
+        ctx.command(0xFF)
+        assert ctx.mode == 0xB1 and not ctx.bank(1).any() and not ctx.get_state().any().item()
+        out = ctx.process(dev(x), continuous=True, want=("filtered",))
+        assert np.array_equal(out["filtered"].cpu().numpy(), g.window(x, rom))
+        ctx.command(0xA1)
+        assert not ctx.process(dev(x), want=("filtered",))["filtered"].any().item()
+
+
+def test_config2_full_size_subset_and_properties(fra, rom):
+    """BASELINE config 2: 4096 independent channels x 16384, state reset per frame.
+    Subset parity on channels {0, 1, C/2, C-1} + 60 seeded random ones; size-independent
+    properties on all of them: Parseval per channel, Hermitian symmetry of the frame."""
+    c, n = 4096, 16384
+    x = fra.synth.tone_noise(c, n, "cuda")
+    with fra.FraContext(c, n) as ctx:
+        ctx.command(0x00)
+        out = ctx.process(x, want=("filtered", "frames", "iq"))
+        assert ctx.last_kernel_count == 2
+        rng = np.random.default_rng(0)
+        pick = np.unique(np.concatenate([[0, 1, c // 2, c - 1], rng.integers(0, c, 60)]))
+        xs = x[pick].cpu().numpy()
+        y, _ = cg.window_iir(xs, rom, 0, g.BANK0_COEFF, B1)
+        assert np.array_equal(out["filtered"][pick].cpu().numpy(), y)
+        iq = out["iq"][pick].cpu().numpy()
+        ref = np.fft.fft(y.astype(np.float64), axis=-1)
+        assert rel_l2(iq[..., 0] + 1j * iq[..., 1], ref) < FFT_TOL
+        # Parseval on every channel: sum |X|^2 = N sum y^2
+        e_t = out["filtered"].to(torch.float64).pow(2).sum(dim=1) * n
+        e_f = out["iq"].to(torch.float64).pow(2).sum(dim=(1, 2))
+        assert torch.allclose(e_t, e_f, rtol=1e-5)
+        # Hermitian symmetry of the fp32 bins: X[N-k] = conj(X[k]) exactly (emitted from the same registers)
+        iqa = out["iq"]
+        assert torch.equal(iqa[:, 1:, 0], iqa[:, 1:, 0].flip(1)) and torch.equal(iqa[:, 1:, 1], -iqa[:, 1:, 1].flip(1))
+        # int16 frame decodes to floor(bins / N)
+        fr = out["frames"].view(torch.int16).view(c, n, 2)
+        want = torch.floor(out["iq"].to(torch.float64) / n).to(torch.int16)
+        assert torch.equal(fr, want)
+
+
+def test_config3_continuous_sharded_channels(fra, rom):
+    """BASELINE config 3 at one GPU's share for 8 GPUs (8192 channels): IIR history
+    carried across frames by the lane-per-channel kernel; splitting the stream in
+    frames must equal the golden model run over the concatenated stream."""
+    c, n, frames = 8192, 16384, 3
+    with fra.FraContext(c, n, flags=fra._abi.FRA_K1_FORCE_LANE) as ctx:
+        ctx.command(0x00)
+        pick = np.array([0, 1, c // 2, c - 1, 777, 4242])
+        st = None
+        for f in range(frames):
+            x = fra.synth.tone_noise(c, n, "cuda", frame=f)
+            out = ctx.process(x, continuous=f > 0, want=("filtered",))
+            y, st = cg.window_iir(x[pick].cpu().numpy(), rom, 0, g.BANK0_COEFF, B1, st)
+            assert np.array_equal(out["filtered"][pick].cpu().numpy(), y)
+        assert np.array_equal(ctx.get_state()[pick].cpu().numpy(), st)
+
+
+def test_config4_dual_banks_reload_and_all_outputs(fra, rom):
+    """BASELINE config 4: bytes A1, then F1 + 12 at a frame boundary mid-run, then 00;
+    int16 I/Q frame + fp32 magnitude + fp32 phase."""
+    c, n = 64, 16384
+    script = [bytes([0xA1]), bytes([0xF1]) + B1.tobytes(), bytes([0x00])]
+    with fra.FraContext(c, n) as ctx:
+        dec = g.CommandDecoder()
+        st = None
+        for f, cmd in enumerate(script):
+            ctx.command(cmd)
+            dec.feed(cmd)
+            x = g.tone_noise(range(c), n=n, seed=10 + f)
+            out = {k: v.cpu().numpy() for k, v in
+                   ctx.process(dev(x), continuous=f > 0, want=("filtered", "frames", "mag", "phase")).items()}
+            y, st = cg.window_iir(x, rom, dec.mode, g.BANK0_COEFF, dec.bank1, st)
+            assert np.array_equal(out["filtered"], y), f
+            re, im, mag = g.decode_frame(out["frames"])
+            assert np.array_equal(mag.view(np.uint32), out["mag"].view(np.uint32))
+            assert np.abs(out["phase"] - np.arctan2(im, re)).max() < 2e-6
+            rq, iq_ = g.quantize_bins(np.fft.fft(y.astype(np.float64), axis=-1), -14)
+            assert np.abs(re - rq).max() <= 1 and np.abs(im - iq_).max() <= 1
+
+
+def test_config5_single_stream(fra, rom):
+    """BASELINE config 5: one long stream.  exact=True is bit-exact (six-lane systolic
+    chain); the time-parallel chunked scan stays within the dead band of the truncating
+    sections and says by how much (it is NOT bit-exact and does not claim to be)."""
+    n = 1 << 20
+    x = g.tone_noise([5], n=n, seed=2)[0]
+    yr, st = cg.window_iir(x[None], rom, 0x00, g.BANK0_COEFF, B1)
+    with fra.FraContext(1, 16384) as ctx:
+        ctx.command(0x00)
+        y, stats = ctx.iir_stream(dev(x), exact=True)
+        assert stats["exact"] == 1 and np.array_equal(y.cpu().numpy(), yr[0])
+        assert np.array_equal(ctx.get_state().cpu().numpy(), st)
+        y, stats = ctx.iir_stream(dev(x), exact=False)
+        assert stats["exact"] == 0 and stats["n_chunks"] > 8 and stats["max_state_dev"] <= 32
+        assert np.abs(y.cpu().numpy().astype(int) - yr[0].astype(int)).max() <= 64
+        # an overflowing (wrapping) cascade is chaotic: the scan detects it and recomputes exactly
+        ctx.load_bank1(B1)
+        ctx.set_mode(0xA1)
+        xr = np.random.default_rng(4).integers(-32768, 32768, 1 << 18).astype(np.int16)
+        yw, _ = cg.window_iir(xr[None], rom, 0xA1, g.BANK0_COEFF, B1)
+        y, stats = ctx.iir_stream(dev(xr), exact=False)
+        assert stats["exact"] == 1 and np.array_equal(y.cpu().numpy(), yw[0])
