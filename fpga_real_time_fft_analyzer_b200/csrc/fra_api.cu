@@ -96,6 +96,7 @@ StageCoef make_stage(const int8_t *k)       // k = B0,B1,B2,A0,A1 (NEW/filter_ii
     c.b2 = (float)k[2] / 128.0f;
     c.na0 = -(float)k[3] / 128.0f;
     c.na1 = -(float)k[4] / 128.0f;
+    c.exp23 = 0x4B000000u;
     return c;
 }
 
@@ -120,7 +121,9 @@ template <int LOG2N, bool WIN, int QMODE>
 int launch_k2_inst(fra_ctx *ctx, const K2Args &args, cudaStream_t st)
 {
     using P = FftPlan<LOG2N>;
-    auto kfn = k2_fft<LOG2N, WIN, QMODE>;
+    // frames-only is the hot configuration and gets its own instantiation
+    const bool frames_only = args.frames && !args.iq && !args.mag && !args.phase;
+    auto kfn = frames_only ? k2_fft<LOG2N, WIN, QMODE, 0> : k2_fft<LOG2N, WIN, QMODE, 1>;
     FRA_TRY(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, P::SMEM_BYTES));
     const int grid = (args.batch + P::FPC - 1) / P::FPC;
     if (grid > 0) {
@@ -223,6 +226,7 @@ int process_range(fra_ctx *ctx, const int16_t *d_in, int c0, int nch, int contin
         k2.phase = o.d_phase;
         k2.qscale = std::ldexp(0.5f, log2_scale);
         k2.batch = nch;
+        k2.exp23 = 0x4B000000u;
         const bool nearest = (ctx->flags & FRA_ROUND_NEAREST) != 0;
         const int qmode = nearest ? 2 : (log2_scale <= -ctx->log2n ? 0 : 1);
         if (ctx->profiling) FRA_TRY(ctx, cudaEventRecord(ctx->ev[2], st));
@@ -680,6 +684,7 @@ int fra_fft_only(fra_ctx *ctx, const int16_t *d_in, int batch, float *d_iq, void
     k2.phase = nullptr;
     k2.qscale = std::ldexp(0.5f, -ctx->log2n);
     k2.batch = batch;
+    k2.exp23 = 0x4B000000u;
     ctx->last_kernels = 0;
     return launch_k2(ctx, k2, /*win=*/false, /*qmode=*/0, st);
 }

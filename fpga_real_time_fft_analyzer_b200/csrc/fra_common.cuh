@@ -40,6 +40,8 @@ constexpr float kBias16 = 8421376.0f;      // 2^23 + 2^15
 struct StageCoef {
     float b2, b1, b0;    //  B2/128 -> x[n],  B1/128 -> x[n-1],  B0/128 -> x[n-2]
     float na0, na1;      // -A0/128 -> y[n-2], -A1/128 -> y[n-1]
+    unsigned exp23;      // 0x4B000000, passed as data so that it lives in a register and
+                         // PRMT's selector can be the immediate (one instruction, no re-materialised selector)
 };
 
 struct CascadeCoef {
@@ -55,26 +57,27 @@ struct StageState {      // registers ve(1), ve(2), vs(1), vs(2) as exact floats
 // offset-binary.  One PRMT splices those 16 bits under the exponent of 2^23 and
 // one FADD removes 2^23 + 2^15: the wrapped int16 as an exact float, with no
 // integer<->float conversion on the recurrence.
-FRA_DEV float wrap16_to_float(float acc)
+FRA_DEV float wrap16_to_float(float acc, unsigned exp23)
 {
     unsigned bits = __float_as_uint(acc);
-    return __uint_as_float(__byte_perm(bits, 0x4B000000u, 0x7610)) - kBias16;
+    return __uint_as_float(__byte_perm(bits, exp23, 0x7610)) - kBias16;
 }
 
 // low 16 bits of the accumulator as two's complement (undo the offset-binary)
 FRA_DEV unsigned acc_to_u16(float acc) { return (__float_as_uint(acc) ^ 0x8000u) & 0xFFFFu; }
 
 // One biquad evaluation, NEW/filter_iir_cust.vhd:96-118 + :133-194 (state shift).
-// Returns the accumulator; *y_out gets the wrapped value as a float.  The y[n-1]
-// term is last: it is the only term on the sample-to-sample recurrence.
+// Returns the accumulator; *y_out gets the wrapped value as a float.  Every partial
+// sum is an exact integer, so the order of the five terms is free: the ones that
+// are known early go first.
 FRA_DEV float biquad_step(float x, const StageCoef &k, StageState &s, float *y_out)
 {
     float acc = __fmaf_rd(s.x2, k.b0, kMagicB);
     acc = __fmaf_rd(s.x1, k.b1, acc);
-    acc = __fmaf_rd(x, k.b2, acc);
     acc = __fmaf_ru(s.y2, k.na0, acc);
-    acc = __fmaf_ru(s.y1, k.na1, acc);
-    float y = wrap16_to_float(acc);
+    acc = __fmaf_rd(x, k.b2, acc);          // x arrives late (previous stage / shuffle): fourth
+    acc = __fmaf_ru(s.y1, k.na1, acc);      // y[n-1] is the recurrence: last
+    float y = wrap16_to_float(acc, k.exp23);
     s.x2 = s.x1; s.x1 = x;
     s.y2 = s.y1; s.y1 = y;
     *y_out = y;
@@ -97,7 +100,7 @@ FRA_DEV float small_int_to_float(int v)
 }
 
 // two packed int16 (little-endian pair) -> ints
-FRA_DEV int lo16(unsigned w) { return (int)(short)(w & 0xFFFFu); }
+FRA_DEV int lo16(unsigned w) { return ((int)(w << 16)) >> 16; }     // shifts, so int->float stays a 32-bit I2FP
 FRA_DEV int hi16(unsigned w) { return ((int)w) >> 16; }
 
 // low 16 bits of two words -> one packed pair (first -> low half)
@@ -107,6 +110,48 @@ FRA_DEV unsigned pack16_acc(float a, float b)
 {
     return __byte_perm(__float_as_uint(a), __float_as_uint(b), 0x5410) ^ 0x80008000u;
 }
+
+// ---- bulk asynchronous global -> shared copies (cp.async.bulk, the TMA engine's
+// 1-D form: SASS UBLKCP) completing on an mbarrier.  One lane issues a whole row.
+#ifdef FRA_HOST_EMUL
+FRA_DEV void mbar_init(uint64_t *, int) {}
+FRA_DEV void mbar_expect_tx(uint64_t *, unsigned) {}
+FRA_DEV void bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *) { std::memcpy(dst, src, bytes); }
+FRA_DEV void mbar_wait(uint64_t *, unsigned) { __syncwarp(); }   // the issuing lanes' memcpy is complete after this
+FRA_DEV void fence_proxy_async() {}
+#else
+FRA_DEV unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+FRA_DEV void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+FRA_DEV void mbar_expect_tx(uint64_t *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+FRA_DEV void bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// bounded wait: a mis-programmed barrier traps instead of hanging the GPU
+FRA_DEV void mbar_wait(uint64_t *bar, unsigned parity)
+{
+    unsigned done = 0;
+    for (unsigned spin = 0; !done; ++spin) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+        if (spin > (1u << 24)) __trap();
+    }
+}
+// orders this thread's generic-proxy shared-memory accesses before later async-proxy (bulk copy) writes
+FRA_DEV void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#endif
 
 FRA_DEV uint4 ldg128(const void *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
 FRA_DEV void stg128(void *p, uint4 v) { *reinterpret_cast<uint4 *>(p) = v; }

@@ -9,8 +9,9 @@
 //   k1_lane   one warp lane per channel, all six stages in the lane's registers.
 //             ~50 issue slots per sample; needs >= ~19k channels to fill 148 SMs.
 //   k1_split  one warp lane per (channel, stage): a warp is five 6-lane systolic
-//             chains, stage s works on sample i-s, outputs pass to the next lane
-//             by __shfl_up.  6x the parallelism for small channel counts (the
+//             chains, stage s works on sample i-4s, outputs pass to the next lane
+//             by __shfl_up three iterations ahead of their use; input rows arrive by
+//             cp.async.bulk (TMA 1-D bulk copies on an mbarrier).  6x the parallelism for small channel counts (the
 //             4096-channel configuration), ~65 issue slots per sample.
 // Both read int16 [C][N] channel-major, write int16 [C][N], and carry the
 // per-stage history (x[n-1], x[n-2], y[n-1], y[n-2]) in state[C][6][4].
@@ -31,7 +32,7 @@ struct K1Args {
 };
 
 // ------------------------------------------------------------------ k1_lane
-constexpr int kLaneBlock = 128;
+constexpr int kLaneBlock = 32;       // one warp per CTA: 2048 warps spread evenly over 148 SMs x 4 schedulers
 
 __global__ void __launch_bounds__(kLaneBlock) k1_lane(K1Args a)
 {
@@ -54,16 +55,22 @@ __global__ void __launch_bounds__(kLaneBlock) k1_lane(K1Args a)
     const int16_t *src = a.in + (size_t)c * a.n;
     int16_t *dst = a.out + (size_t)c * a.n;
 
+    // software prefetch: the next 16 samples are requested before the current 16 are filtered
+    uint4 xa = ldg128(src), xb = ldg128(src + 8);
     for (int n0 = 0; n0 < a.n; n0 += 16) {
-        uint4 xa = ldg128(src + n0);
-        uint4 xb = ldg128(src + n0 + 8);
         const unsigned xw[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+        if (n0 + 16 < a.n) {
+            xa = ldg128(src + n0 + 16);
+            xb = ldg128(src + n0 + 24);
+        }
         const int4 *rp = reinterpret_cast<const int4 *>(a.rom32 + (n0 & (kWindowLen - 1)));
+        int4 rr[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) rr[q] = __ldg(rp + q);   // warp-uniform address: one L1 broadcast each
         unsigned ow[8];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            int4 r = __ldg(rp + q);                       // warp-uniform address: one L1 broadcast
-            const int rom[4] = {r.x, r.y, r.z, r.w};
+            const int rom[4] = {rr[q].x, rr[q].y, rr[q].z, rr[q].w};
             float acc[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -98,45 +105,60 @@ constexpr int kSplitGroups = 5;      // channels per warp (5 x 6 = 30 lanes, 2 i
 constexpr int kSplitChunk = 256;     // samples staged per chunk
 constexpr int kSplitWarps = 4;       // warps per CTA
 constexpr int kSplitRing = 2 * kSplitChunk;
-constexpr int kSplitSmemPerWarp =
-    kSplitGroups * kSplitChunk * (int)sizeof(float) + kSplitGroups * kSplitRing * (int)sizeof(int16_t);
+constexpr int kSplitWinStride = kSplitChunk + 4;    // floats; +16 B so the five rows start in different banks
+constexpr int kSplitRingStride = kSplitRing + 8;    // int16;  +16 B, same reason
+constexpr int kSplitRawBytes = kSplitGroups * kSplitChunk * 2;
+constexpr int kSplitWinBytes = kSplitGroups * kSplitWinStride * 4;
+constexpr int kSplitRingBytes = kSplitGroups * kSplitRingStride * 2;
+constexpr int kSplitSmemPerWarp = ((kSplitRawBytes + kSplitWinBytes + kSplitRingBytes + 16 + 127) / 128) * 128;
+
+constexpr int kSkew = 4;             // iterations between a stage and the next one (shuffle latency hiding)
+constexpr int kSplitDelay = (kStages - 1) * kSkew;   // the last stage emits sample i - 20 at iteration i
 
 struct SplitLane {
     StageCoef k;
     StageState st;
-    float y;            // this lane's latest output, read by lane+1 next iteration
-    unsigned carry[3];  // accumulator bits of the 3 newest outputs not yet stored
-    int s;              // stage 0..5
+    float y;                // this lane's latest output
+    float up[kSkew - 1];    // lane-1's outputs in flight: up[0] is this iteration's input
+    unsigned carry[4];      // accumulator bits of the 4 newest outputs not yet stored
+    int s;                  // stage 0..5
     bool first, last;
 };
 
-// Eight systolic iterations i_base .. i_base+7.  Lane (g, s) processes sample
-// i - s at iteration i.  GUARD = true for the blocks that contain samples outside
-// [0, n): the first block of a frame (stages still empty) and the flush block.
-template <bool GUARD>
-FRA_DEV void split_block8(SplitLane &L, int i_base, int n, const float *win8, int16_t *ring_row, bool store_ok)
+FRA_DEV void split_load_w(const float *p, float (&w)[16])
 {
-    float w[8];
-    if (win8 != nullptr) {
-        const float4 w0 = *reinterpret_cast<const float4 *>(win8);
-        const float4 w1 = *reinterpret_cast<const float4 *>(win8 + 4);
-        w[0] = w0.x; w[1] = w0.y; w[2] = w0.z; w[3] = w0.w;
-        w[4] = w1.x; w[5] = w1.y; w[6] = w1.z; w[7] = w1.w;
-    } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) w[j] = 0.0f;
+    for (int q = 0; q < 4; ++q) {
+        const float4 v = *reinterpret_cast<const float4 *>(p + 4 * q);
+        w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
     }
-    unsigned ob[8];
+}
+
+// Sixteen systolic iterations i_base .. i_base+15.  Lane (g, s) processes sample
+// i - kSkew*s at iteration i.  The skew is kSkew = 4 iterations per stage: the
+// shuffle that carries stage s-1's output to stage s is issued three iterations
+// before its result is consumed, so its ~30-cycle latency (plus the select and the
+// two FFMAs behind it) fits in the slack and the per-iteration critical path is
+// only the lane's own y[n-1] recurrence (FFMA -> PRMT -> FADD).  GUARD = true for
+// the blocks that contain samples outside [0, n): the first two blocks of a frame
+// (stages still empty) and the two flush blocks.
+template <bool GUARD>
+FRA_DEV void split_block16(SplitLane &L, int i_base, int n, const float (&w)[16], int16_t *ring_row, bool store_ok)
+{
+    unsigned ob[16];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        float up = __shfl_up_sync(0xffffffffu, L.y, 1);
-        float x = L.first ? w[j] : up;
+    for (int j = 0; j < 16; ++j) {
+        const float up_new = __shfl_up_sync(0xffffffffu, L.y, 1);   // consumed kSkew - 1 iterations from now
+        const float x = L.first ? w[j] : L.up[0];
+#pragma unroll
+        for (int q = 0; q + 1 < kSkew - 1; ++q) L.up[q] = L.up[q + 1];
+        L.up[kSkew - 2] = up_new;
         if (GUARD) {
             StageState keep = L.st;
             float ykeep = L.y;
             float y;
             float acc = biquad_step(x, L.k, L.st, &y);
-            bool active = (unsigned)(i_base + j - L.s) < (unsigned)n;
+            bool active = (unsigned)(i_base + j - kSkew * L.s) < (unsigned)n;
             if (active) {
                 L.y = y;
             } else {
@@ -149,16 +171,24 @@ FRA_DEV void split_block8(SplitLane &L, int i_base, int n, const float *win8, in
             ob[j] = __float_as_uint(acc);
         }
     }
-    // the last-stage lane emitted samples i_base-5 .. i_base+2; together with the
-    // carry (i_base-8 .. i_base-6) that completes the aligned group [i_base-8, i_base-1]
-    uint4 o;
-    o.x = __byte_perm(L.carry[0], L.carry[1], 0x5410) ^ 0x80008000u;
-    o.y = __byte_perm(L.carry[2], ob[0], 0x5410) ^ 0x80008000u;
-    o.z = __byte_perm(ob[1], ob[2], 0x5410) ^ 0x80008000u;
-    o.w = __byte_perm(ob[3], ob[4], 0x5410) ^ 0x80008000u;
-    L.carry[0] = ob[5]; L.carry[1] = ob[6]; L.carry[2] = ob[7];
-    if (store_ok && L.last && i_base >= 8)
-        *reinterpret_cast<uint4 *>(ring_row + ((i_base - 8) & (kSplitRing - 1))) = o;
+    // the last-stage lane emitted samples i_base-20 .. i_base-5; with the carry
+    // (i_base-24 .. i_base-21) that completes the aligned groups [i_base-24, i_base-17]
+    // and [i_base-16, i_base-9].  Still offset-binary: the flush flips the sign bits.
+    uint4 g1, g2;
+    g1.x = __byte_perm(L.carry[0], L.carry[1], 0x5410);
+    g1.y = __byte_perm(L.carry[2], L.carry[3], 0x5410);
+    g1.z = __byte_perm(ob[0], ob[1], 0x5410);
+    g1.w = __byte_perm(ob[2], ob[3], 0x5410);
+    g2.x = __byte_perm(ob[4], ob[5], 0x5410);
+    g2.y = __byte_perm(ob[6], ob[7], 0x5410);
+    g2.z = __byte_perm(ob[8], ob[9], 0x5410);
+    g2.w = __byte_perm(ob[10], ob[11], 0x5410);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) L.carry[j] = ob[12 + j];
+    if (store_ok && L.last) {
+        if (i_base >= 24 && i_base - 16 <= n) *reinterpret_cast<uint4 *>(ring_row + ((i_base - 24) & (kSplitRing - 1))) = g1;
+        if (i_base >= 16 && i_base - 8 <= n) *reinterpret_cast<uint4 *>(ring_row + ((i_base - 16) & (kSplitRing - 1))) = g2;
+    }
 }
 
 __global__ void __launch_bounds__(kSplitWarps * 32) k1_split(K1Args a)
@@ -171,8 +201,11 @@ __global__ void __launch_bounds__(kSplitWarps * 32) k1_split(K1Args a)
     if (c_base >= a.channels) return;                       // warp-uniform; no block-wide barrier is used
     const int n_ch = min(kSplitGroups, a.channels - c_base);
 
-    float *win = reinterpret_cast<float *>(smem_raw + (size_t)warp_in_cta * kSplitSmemPerWarp);   // [5][256]
-    int16_t *ring = reinterpret_cast<int16_t *>(win + kSplitGroups * kSplitChunk);                 // [5][512]
+    unsigned char *wbase = smem_raw + (size_t)warp_in_cta * kSplitSmemPerWarp;
+    int16_t *raw = reinterpret_cast<int16_t *>(wbase);                                   // [5][256] int16, bulk-copy target
+    float *win = reinterpret_cast<float *>(wbase + kSplitRawBytes);                      // [5][260] windowed samples
+    int16_t *ring = reinterpret_cast<int16_t *>(wbase + kSplitRawBytes + kSplitWinBytes);  // [5][520] output ring
+    uint64_t *bar = reinterpret_cast<uint64_t *>(wbase + kSplitRawBytes + kSplitWinBytes + kSplitRingBytes);
 
     const int g_raw = lane / kStages;
     const int g = min(g_raw, kSplitGroups - 1);
@@ -183,7 +216,10 @@ __global__ void __launch_bounds__(kSplitWarps * 32) k1_split(K1Args a)
     L.last = (L.s == kStages - 1);
     L.k = a.coef.set[L.s & 1];
     L.y = 0.0f;
-    L.carry[0] = L.carry[1] = L.carry[2] = 0u;
+#pragma unroll
+    for (int j = 0; j < kSkew - 1; ++j) L.up[j] = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) L.carry[j] = 0u;
     {
         uint2 v = make_uint2(0u, 0u);
         if (a.continuous && lane_valid)
@@ -194,78 +230,97 @@ __global__ void __launch_bounds__(kSplitWarps * 32) k1_split(K1Args a)
         L.st.y2 = small_int_to_float(hi16(v.y));
     }
 
-    // staging map: lane handles samples [4*lane, +4) and [128 + 4*lane, +4) of every row
-    uint2 pre[kSplitGroups][2];
+    if (lane == 0) mbar_init(bar, 1);
+    __syncwarp();
+    unsigned phase = 0;
+
+    // input staging: one 512-byte bulk copy (cp.async.bulk) per channel row, issued by
+    // lanes 0..n_ch-1, landing in `raw` while the previous chunk is being filtered
+    int4 rom_a, rom_b;            // window coefficients of the chunk in flight, fetched with it
     auto prefetch = [&](int i0) {
+        rom_a = __ldg(reinterpret_cast<const int4 *>(a.rom32 + ((i0 + 4 * lane) & (kWindowLen - 1))));
+        rom_b = __ldg(reinterpret_cast<const int4 *>(a.rom32 + ((i0 + 128 + 4 * lane) & (kWindowLen - 1))));
+        if (lane == 0) mbar_expect_tx(bar, (unsigned)(n_ch * kSplitChunk * 2));
+        if (lane < n_ch)
+            bulk_g2s(raw + lane * kSplitChunk, a.in + (size_t)(c_base + lane) * a.n + i0, kSplitChunk * 2, bar);
+    };
+    // raw int16 -> window -> float; lane handles samples [4*lane, +4) and [128 + 4*lane, +4) of every row
+    auto convert = [&]() {
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+        const int4 ra = rom_a, rb = rom_b;
 #pragma unroll
         for (int r = 0; r < kSplitGroups; ++r) {
-            pre[r][0] = make_uint2(0u, 0u);
-            pre[r][1] = make_uint2(0u, 0u);
+            uint2 pa = make_uint2(0u, 0u), pb = make_uint2(0u, 0u);
             if (r < n_ch) {
-                const int16_t *row = a.in + (size_t)(c_base + r) * a.n + i0;
-                pre[r][0] = __ldg(reinterpret_cast<const uint2 *>(row + 4 * lane));
-                pre[r][1] = __ldg(reinterpret_cast<const uint2 *>(row + 128 + 4 * lane));
+                pa = *reinterpret_cast<const uint2 *>(raw + r * kSplitChunk + 4 * lane);
+                pb = *reinterpret_cast<const uint2 *>(raw + r * kSplitChunk + 128 + 4 * lane);
             }
-        }
-    };
-    auto convert = [&](int i0) {
-        const int w0 = (i0 + 4 * lane) & (kWindowLen - 1);
-        const int w1 = (i0 + 128 + 4 * lane) & (kWindowLen - 1);
-        const int4 ra = __ldg(reinterpret_cast<const int4 *>(a.rom32 + w0));
-        const int4 rb = __ldg(reinterpret_cast<const int4 *>(a.rom32 + w1));
-#pragma unroll
-        for (int r = 0; r < kSplitGroups; ++r) {
             float4 fa, fb;
-            fa.x = small_int_to_float(window_int(lo16(pre[r][0].x), ra.x));
-            fa.y = small_int_to_float(window_int(hi16(pre[r][0].x), ra.y));
-            fa.z = small_int_to_float(window_int(lo16(pre[r][0].y), ra.z));
-            fa.w = small_int_to_float(window_int(hi16(pre[r][0].y), ra.w));
-            fb.x = small_int_to_float(window_int(lo16(pre[r][1].x), rb.x));
-            fb.y = small_int_to_float(window_int(hi16(pre[r][1].x), rb.y));
-            fb.z = small_int_to_float(window_int(lo16(pre[r][1].y), rb.z));
-            fb.w = small_int_to_float(window_int(hi16(pre[r][1].y), rb.w));
-            *reinterpret_cast<float4 *>(win + r * kSplitChunk + 4 * lane) = fa;
-            *reinterpret_cast<float4 *>(win + r * kSplitChunk + 128 + 4 * lane) = fb;
+            fa.x = small_int_to_float(window_int(lo16(pa.x), ra.x));
+            fa.y = small_int_to_float(window_int(hi16(pa.x), ra.y));
+            fa.z = small_int_to_float(window_int(lo16(pa.y), ra.z));
+            fa.w = small_int_to_float(window_int(hi16(pa.y), ra.w));
+            fb.x = small_int_to_float(window_int(lo16(pb.x), rb.x));
+            fb.y = small_int_to_float(window_int(hi16(pb.x), rb.y));
+            fb.z = small_int_to_float(window_int(lo16(pb.y), rb.z));
+            fb.w = small_int_to_float(window_int(hi16(pb.y), rb.w));
+            *reinterpret_cast<float4 *>(win + r * kSplitWinStride + 4 * lane) = fa;
+            *reinterpret_cast<float4 *>(win + r * kSplitWinStride + 128 + 4 * lane) = fb;
         }
+        fence_proxy_async();       // my reads of `raw` are done before the next bulk copy may overwrite it
+        __syncwarp();
     };
-    // store the finished output group [m0, m0 + 256) from the ring (m0 may be -8)
+    // store the finished output groups [m0, m0 + 8 * count8) from the ring (m0 may be negative)
     auto flush = [&](int m0, int count8) {
 #pragma unroll
         for (int r = 0; r < kSplitGroups; ++r) {
             const int m = m0 + 8 * lane;
             if (r < n_ch && lane < count8 && m >= 0) {
-                uint4 v = *reinterpret_cast<const uint4 *>(ring + r * kSplitRing + (m & (kSplitRing - 1)));
+                uint4 v = *reinterpret_cast<const uint4 *>(ring + r * kSplitRingStride + (m & (kSplitRing - 1)));
+                v.x ^= 0x80008000u; v.y ^= 0x80008000u; v.z ^= 0x80008000u; v.w ^= 0x80008000u;   // offset-binary -> two's complement
                 stg128(a.out + (size_t)(c_base + r) * a.n + m, v);
             }
         }
     };
 
     prefetch(0);
-    convert(0);
-    __syncwarp();
-    const float *win_row = win + g * kSplitChunk;
-    int16_t *ring_row = ring + g * kSplitRing;
+    convert();
+    const float *win_row = win + g * kSplitWinStride;
+    int16_t *ring_row = ring + g * kSplitRingStride;
+    float wa[16], wb[16];
 
     for (int i0 = 0; i0 < a.n; i0 += kSplitChunk) {
         const bool more = (i0 + kSplitChunk) < a.n;
         if (more) prefetch(i0 + kSplitChunk);
+        int b = 0;
+        split_load_w(win_row, wa);
         if (i0 == 0) {
-            split_block8<true>(L, 0, a.n, win_row, ring_row, lane_valid);
-            for (int b = 8; b < kSplitChunk; b += 8)
-                split_block8<false>(L, b, a.n, win_row + b, ring_row, lane_valid);
-        } else {
-            for (int b = 0; b < kSplitChunk; b += 8)
-                split_block8<false>(L, i0 + b, a.n, win_row + b, ring_row, lane_valid);
+            split_load_w(win_row + 16, wb);
+            split_block16<true>(L, 0, a.n, wa, ring_row, lane_valid);
+            split_load_w(win_row + 32, wa);
+            split_block16<true>(L, 16, a.n, wb, ring_row, lane_valid);
+            b = 32;
+        }
+        // two blocks per trip: the samples of block b+16 are fetched while block b runs
+        for (; b < kSplitChunk; b += 32) {
+            split_load_w(win_row + b + 16, wb);
+            split_block16<false>(L, i0 + b, a.n, wa, ring_row, lane_valid);
+            if (b + 32 < kSplitChunk) split_load_w(win_row + b + 32, wa);
+            split_block16<false>(L, i0 + b + 16, a.n, wb, ring_row, lane_valid);
         }
         __syncwarp();
-        flush(i0 - 8, kSplitChunk / 8);
-        if (more) convert(i0 + kSplitChunk);
+        flush(i0 - 24, kSplitChunk / 8);
         __syncwarp();
+        if (more) convert();
     }
-    // flush block: iterations n .. n+7 drain stages 1..5 and complete group [n-8, n-1]
-    split_block8<true>(L, a.n, a.n, nullptr, ring_row, lane_valid);
+    // flush blocks: iterations n .. n+31 drain stages 1..5 and complete the groups up to [n-8, n-1]
+#pragma unroll
+    for (int j = 0; j < 16; ++j) wa[j] = 0.0f;
+    split_block16<true>(L, a.n, a.n, wa, ring_row, lane_valid);
+    split_block16<true>(L, a.n + 16, a.n, wa, ring_row, lane_valid);
     __syncwarp();
-    flush(a.n - 8, 1);
+    flush(a.n - 24, 3);
 
     if (lane_valid) {
         uint2 v;

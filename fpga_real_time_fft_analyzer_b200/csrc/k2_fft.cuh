@@ -34,6 +34,7 @@ struct K2Args {
     float *phase;           // [B][N] or null
     float qscale;           // 0.5 * 2^log2_scale (the untangle leaves 2 X[k])
     int batch;
+    unsigned exp23;         // 0x4B000000 as data (keeps PRMT's selector an immediate)
 };
 
 template <int LOG2N>
@@ -51,6 +52,15 @@ struct FftPlan {
     static constexpr int SLOTS = FPC * (L / 2);                 // last-pass work items per CTA
 };
 
+// two packed int16 -> two exact floats with no conversion instruction: flip the sign
+// bits (offset-binary), splice each half under the exponent of 2^23, subtract 2^23 + 2^15
+FRA_DEV float2 int16_pair_to_float2(unsigned w, unsigned exp23)
+{
+    const unsigned u = w ^ 0x80008000u;
+    return make_float2(__uint_as_float(__byte_perm(u, exp23, 0x7610)) - kBias16,
+                       __uint_as_float(__byte_perm(u, exp23, 0x7632)) - kBias16);
+}
+
 FRA_DEV float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 FRA_DEV float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 FRA_DEV float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
@@ -58,9 +68,13 @@ FRA_DEV float2 cmulc(float2 a, float2 b) { return make_float2(a.x * b.x + a.y * 
 FRA_DEV float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 FRA_DEV float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }     // a * (-i)
 
-// shared-memory index swizzle (complex-element units): makes the stride-16 and
-// stride-256 scatter of the Stockham passes bank-conflict-free for 8-byte accesses
-FRA_DEV int swz(int idx) { return idx ^ ((idx >> 4) & 15); }
+// shared-memory index swizzle (complex-element units, 8 B): within every 128-byte row
+// of 16 elements the 16-byte chunk index is XORed with the row number mod 8.  The
+// stride-16 scatter of pass 0 (as 16-byte vector stores), the stride-16 scatter of
+// pass 1 and every unit-stride read are then bank-conflict-free, and because
+// 256 r shifts the row by a multiple of 8, swz(b + 256 r) = swz(b) + 256 r: one
+// swizzled base per thread and immediate offsets for the 16 butterfly inputs.
+FRA_DEV int swz(int idx) { return idx ^ (((idx >> 4) & 7) << 1); }
 
 FRA_DEV void dft4(float2 &a0, float2 &a1, float2 &a2, float2 &a3)
 {
@@ -192,10 +206,13 @@ FRA_DEV float2 w16(int q)
     }
 }
 
-template <int LOG2N, bool WIN, int QMODE>
-__global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS) k2_fft(K2Args a)
+// OUT = 0: int16 frames only (the hot configuration); OUT = 1: any combination of
+// outputs, selected at run time by the null pointers in K2Args.
+template <int LOG2N, bool WIN, int QMODE, int OUT>
+__global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS, (LOG2N == 15) ? 1 : 2) k2_fft(K2Args a)
 {
     using P = FftPlan<LOG2N>;
+    constexpr int IPT = P::ITEMS / P::THREADS;          // butterflies per thread per pass (2)
     FRA_DYN_SMEM(smem_raw);
     float2 *buf = reinterpret_cast<float2 *>(smem_raw);
     const int tid = threadIdx.x;
@@ -204,11 +221,11 @@ __global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS) k2_fft(K2Args a)
     // ---------------------------------------------- radix-16 Stockham passes
 #pragma unroll 1
     for (int pass = 0; pass < P::PASSES; ++pass) {
-        const int ns = (pass == 0) ? 1 : (pass == 1 ? 16 : 256);
-        float2 o[P::ITEMS / P::THREADS][16];
-        int obase[P::ITEMS / P::THREADS];
+        float2 o[IPT][16];
+        int wbase[IPT];                                    // swizzled base of this butterfly's outputs
+        int jlow[IPT];
 #pragma unroll
-        for (int q = 0; q < P::ITEMS / P::THREADS; ++q) {
+        for (int q = 0; q < IPT; ++q) {
             const int it = tid + P::THREADS * q;
             const int j = it % P::NB;
             const int f = (it / P::NB) % P::F;
@@ -218,49 +235,75 @@ __global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS) k2_fft(K2Args a)
             if (pass == 0) {
                 const int frame = frame0 + fr;
                 const bool live = frame < a.batch;
-                const uint32_t *src = a.in + (size_t)frame * P::M;
+                const uint32_t *src = a.in + (size_t)frame * P::M + (P::F * j + f);
 #pragma unroll
                 for (int r = 0; r < 16; ++r) {
-                    const int e = P::F * (j + P::NB * r) + f;        // complex index in z
-                    const unsigned w = live ? __ldg(src + e) : 0u;
-                    int x0 = lo16(w), x1 = hi16(w);
+                    const unsigned w = live ? __ldg(src + P::F * P::NB * r) : 0u;   // z[F (j + NB r) + f]
                     if (WIN) {
+                        const int e = P::F * (j + P::NB * r) + f;
                         const int2 c = __ldg(reinterpret_cast<const int2 *>(a.rom32 + ((2 * e) & (kWindowLen - 1))));
-                        x0 = window_int(x0, c.x);
-                        x1 = window_int(x1, c.y);
+                        v[r] = make_float2(small_int_to_float(window_int(lo16(w), c.x)),
+                                           small_int_to_float(window_int(hi16(w), c.y)));
+                    } else {
+                        v[r] = int16_pair_to_float2(w, a.exp23);
                     }
-                    v[r] = make_float2(small_int_to_float(x0), small_int_to_float(x1));
                 }
+                wbase[q] = base + 16 * j;                  // out[16 j + r]
+                jlow[q] = j & 7;
             } else {
+                const int ns = (pass == 1) ? 16 : 256;
                 const int k = j % ns;
                 const float2 *tw = (pass == 1) ? (a.tw1 + k) : (a.tw2 + k);
                 const int tws = (pass == 1) ? 16 : 256;
+                float2 t[16];
+#pragma unroll
+                for (int r = 1; r < 16; ++r) t[r] = __ldg(tw + r * tws);
+                // in[j + NB r].  NB = 256: 256 r is a whole number of 8-row groups, one swizzled base.
+                // NB = 16 (L = 256): j < 16 is the column, row r: chunk XOR is r & 7.
+                const float2 *p = buf + swz(base + j);
+                const float2 *prow = buf + base;
 #pragma unroll
                 for (int r = 0; r < 16; ++r) {
-                    float2 x = buf[swz(base + j + P::NB * r)];
-                    if (r > 0) x = cmul(x, __ldg(tw + r * tws));
-                    v[r] = x;
+                    const float2 x = (P::NB == 256) ? p[256 * r] : prow[16 * r + (j ^ ((r & 7) << 1))];
+                    v[r] = (r > 0) ? cmul(x, t[r]) : x;
                 }
+                wbase[q] = base + (j / ns) * ns * 16 + k;  // out[.. + r ns]
+                jlow[q] = k;
             }
             dft16(v, o[q]);
-            const int k = j % ns;
-            obase[q] = base + (j / ns) * ns * 16 + k;
         }
         // pass 0 reads global memory only; the last pass of each size writes back
         // to the positions it read.  Only the middle pass of L = 4096 scatters into
         // other threads' read positions and needs the barrier between read and write.
         if (pass == 1 && P::PASSES == 3) __syncthreads();
 #pragma unroll
-        for (int q = 0; q < P::ITEMS / P::THREADS; ++q) {
+        for (int q = 0; q < IPT; ++q) {
+            if (pass == 0) {
+                // 16 consecutive elements = one 128-byte row: eight 16-byte stores, chunk c -> c ^ (row & 7)
+                float4 *row = reinterpret_cast<float4 *>(buf + wbase[q]);
 #pragma unroll
-            for (int r = 0; r < 16; ++r) buf[swz(obase[q] + r * ns)] = o[q][r];
+                for (int c = 0; c < 8; ++c)
+                    row[c ^ jlow[q]] = make_float4(o[q][2 * c].x, o[q][2 * c].y, o[q][2 * c + 1].x, o[q][2 * c + 1].y);
+            } else if (pass == 1) {
+                // out[w + 16 r], w = (8-row-aligned) + k with k < 16: row advances by r, chunk XOR is r & 7
+                float2 *prow = buf + (wbase[q] - jlow[q]);
+#pragma unroll
+                for (int r = 0; r < 16; ++r) prow[16 * r + (jlow[q] ^ ((r & 7) << 1))] = o[q][r];
+            } else {
+                float2 *p = buf + swz(wbase[q]);           // out[j + 256 r]: same positions as read
+#pragma unroll
+                for (int r = 0; r < 16; ++r) p[256 * r] = o[q][r];
+            }
         }
         __syncthreads();
     }
 
     // ---------------- last pass: radix-F combine + untangle + mirror + pack
     BinOut out;
-    out.frames = a.frames; out.iq = a.iq; out.mag = a.mag; out.phase = a.phase; out.qscale = a.qscale;
+    out.frames = a.frames; out.qscale = a.qscale;
+    out.iq = (OUT == 0) ? nullptr : a.iq;
+    out.mag = (OUT == 0) ? nullptr : a.mag;
+    out.phase = (OUT == 0) ? nullptr : a.phase;
 #pragma unroll 1
     for (int slot = tid; slot < P::SLOTS; slot += P::THREADS) {
         const int fr = slot / (P::L / 2);
@@ -273,14 +316,18 @@ __global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS) k2_fft(K2Args a)
         for (int rep = 0; rep < reps; ++rep) {
             const int k = rep ? (P::L / 2) : k0;
             const int km = (P::L - k) & (P::L - 1);
+            const float2 wn = __ldg(a.twn + k);                            // W_N^k
+            const float2 *pk = buf + fr * P::M + swz(k);                   // f L is a multiple of 8 rows
+            const float2 *pm = buf + fr * P::M + swz(km);
             float2 za[P::F], zb[P::F];
 #pragma unroll
             for (int f = 0; f < P::F; ++f) {
-                const int base = fr * P::M + f * P::L;
-                za[f] = buf[swz(base + k)];
-                zb[f] = buf[swz(base + km)];
+                za[f] = pk[f * P::L];
+                zb[f] = pm[f * P::L];
                 if (f > 0) {
-                    const float2 w = __ldg(a.twn + 2 * f * k);             // W_M^(f k)
+                    // W_M^(f k) = W_N^(2 f k); f = 1 by squaring W_N^k, saving a load
+                    const float2 w = (f == 1) ? make_float2(wn.x * wn.x - wn.y * wn.y, 2.0f * wn.x * wn.y)
+                                              : __ldg(a.twn + 2 * f * k);
                     za[f] = cmul(za[f], w);
                     // W_M^(f (L-k)) = W_F^f * conj(W_M^(f k))
                     float2 t = cmulc(zb[f], w);
@@ -305,7 +352,6 @@ __global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS) k2_fft(K2Args a)
             }
             dft_small<P::F>(za);       // za[q] = Z[k + L q]
             dft_small<P::F>(zb);       // zb[q] = Z[(L - k) + L q]
-            const float2 wn = __ldg(a.twn + k);                            // W_N^k
 #pragma unroll
             for (int q = 0; q < P::F; ++q) {
                 const float2 A = za[q];

@@ -1,0 +1,39 @@
+#!/usr/bin/env python3
+"""Runs a few steps of the hot path for ncu / timing (not a benchmark).
+usage: prof_step.py [--channels C] [--steps K] [--mode 0x00|0xB1] [--k1 auto|lane|split] [--time]"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from fpga_real_time_fft_analyzer_b200 import FraContext, _abi, synth  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--channels", type=int, default=4096)
+ap.add_argument("--n", type=int, default=16384)
+ap.add_argument("--steps", type=int, default=4)
+ap.add_argument("--mode", default="0x00")
+ap.add_argument("--k1", default="auto")
+ap.add_argument("--time", action="store_true")
+a = ap.parse_args()
+flags = {"auto": 0, "lane": _abi.FRA_K1_FORCE_LANE, "split": _abi.FRA_K1_FORCE_SPLIT}[a.k1]
+ctx = FraContext(a.channels, a.n, flags=flags)
+ctx.command(int(a.mode, 16))
+xs = [synth.tone_noise(a.channels, a.n, "cuda", frame=i) for i in range(2)]
+out = {"frames": torch.empty((a.channels, 4 * a.n), dtype=torch.uint8, device="cuda")}
+ctx.profile(True)
+k1, k2 = [], []
+for i in range(a.steps):
+    ctx.process(xs[i % 2], want=("frames",), out=out)
+    if a.time:
+        t = ctx.profile_last()
+        k1.append(t[0]); k2.append(t[1])
+torch.cuda.synchronize()
+if a.time:
+    s = a.channels * a.n / 1e9
+    m1, m2 = min(k1[1:]), min(k2[1:])
+    print(f"channels={a.channels} n={a.n} mode={a.mode} k1={a.k1}: K1 {m1:.4f} ms ({s / m1 * 1e3 if m1 else 0:.1f} Gs/s)  "
+          f"K2 {m2:.4f} ms ({s / m2 * 1e3:.1f} Gs/s)  chain {s / (m1 + m2) * 1e3:.1f} Gs/s")
+print("done")
