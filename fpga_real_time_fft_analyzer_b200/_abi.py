@@ -30,6 +30,7 @@ FRA_SCALE_DEFAULT = 0x7FFFFFFF
 FRA_ROUND_NEAREST = 0x1
 FRA_K1_FORCE_LANE = 0x2
 FRA_K1_FORCE_SPLIT = 0x4
+FRA_K1_SPECULATE = 0x8
 
 
 class FraOutputs(C.Structure):

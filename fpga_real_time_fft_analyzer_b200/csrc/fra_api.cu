@@ -181,6 +181,7 @@ int process_range(fra_ctx *ctx, const int16_t *d_in, int c0, int nch, int contin
         k1.channels = nch;
         k1.n = n;
         k1.continuous = continuous;
+        k1.speculate = (ctx->flags & FRA_K1_SPECULATE) ? 1 : 0;
         if (ctx->profiling) FRA_TRY(ctx, cudaEventRecord(ctx->ev[0], st));
         bool split = nch < kLaneMinChannels;
         if (ctx->flags & FRA_K1_FORCE_LANE) split = false;
@@ -588,6 +589,7 @@ int fra_iir_stream(fra_ctx *ctx, const int16_t *d_in, int16_t *d_out, size_t n, 
         k1.channels = 1;
         k1.n = (int)n;
         k1.continuous = continuous;
+        k1.speculate = (ctx->flags & FRA_K1_SPECULATE) ? 1 : 0;
         const size_t smem = (size_t)kSplitWarps * kSplitSmemPerWarp;
         auto kfn = k1_split;
         FRA_TRY(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -84,6 +84,26 @@ FRA_DEV float biquad_step(float x, const StageCoef &k, StageState &s, float *y_o
     return acc;
 }
 
+// Speculative form of the same step for the latency-bound systolic kernel: assume the
+// five-term sum does not leave the int16 range (true unless the filter overflows), so
+// y = acc - kMagicB exactly and the recurrence is FFMA -> FADD instead of
+// FFMA -> PRMT -> FADD.  *absmax tracks |y|; the caller re-runs the block with
+// biquad_step when any |y| > 32767 was seen, so the result is always the exact one.
+FRA_DEV float biquad_step_spec(float x, const StageCoef &k, StageState &s, float *y_out, float *absmax)
+{
+    float acc = __fmaf_rd(s.x2, k.b0, kMagicB);
+    acc = __fmaf_rd(s.x1, k.b1, acc);
+    acc = __fmaf_ru(s.y2, k.na0, acc);
+    acc = __fmaf_rd(x, k.b2, acc);
+    acc = __fmaf_ru(s.y1, k.na1, acc);
+    float y = acc - kMagicB;
+    *absmax = fmaxf(*absmax, fabsf(y));
+    s.x2 = s.x1; s.x1 = x;
+    s.y2 = s.y1; s.y1 = y;
+    *y_out = y;
+    return acc;
+}
+
 // hann_window arithmetic, NEW/hann8192.vhd:36-39: 32-bit product, +2^14, >>15 is
 // product(31 downto 15) + product(14); numeric_std resize keeps sign + low 15
 // bits, so the only out-of-range value (+32768 for x = c = -32768) becomes 0.

@@ -29,6 +29,7 @@ struct K1Args {
     int channels;
     int n;                  // samples per frame, multiple of 256
     int continuous;
+    int speculate;          // k1_split: try the no-overflow recurrence first (rolled back when it was wrong)
 };
 
 // ------------------------------------------------------------------ k1_lane
@@ -105,11 +106,12 @@ constexpr int kSplitGroups = 5;      // channels per warp (5 x 6 = 30 lanes, 2 i
 constexpr int kSplitChunk = 256;     // samples staged per chunk
 constexpr int kSplitWarps = 4;       // warps per CTA
 constexpr int kSplitRing = 2 * kSplitChunk;
-constexpr int kSplitWinStride = kSplitChunk + 4;    // floats; +16 B so the five rows start in different banks
+constexpr int kSplitWinStride = kSplitChunk + 20;   // floats; rows start in different banks, and the look-ahead
+                                                    // load of the block after the last one stays inside the row
 constexpr int kSplitRingStride = kSplitRing + 8;    // int16;  +16 B, same reason
 constexpr int kSplitRawBytes = kSplitGroups * kSplitChunk * 2;
 constexpr int kSplitWinBytes = kSplitGroups * kSplitWinStride * 4;
-constexpr int kSplitRingBytes = kSplitGroups * kSplitRingStride * 2;
+constexpr int kSplitRingBytes = (kSplitGroups + 1) * kSplitRingStride * 2;   // + one dummy row: every lane stores, no divergence
 constexpr int kSplitSmemPerWarp = ((kSplitRawBytes + kSplitWinBytes + kSplitRingBytes + 16 + 127) / 128) * 128;
 
 constexpr int kSkew = 4;             // iterations between a stage and the next one (shuffle latency hiding)
@@ -142,10 +144,11 @@ FRA_DEV void split_load_w(const float *p, float (&w)[16])
 // only the lane's own y[n-1] recurrence (FFMA -> PRMT -> FADD).  GUARD = true for
 // the blocks that contain samples outside [0, n): the first two blocks of a frame
 // (stages still empty) and the two flush blocks.
-template <bool GUARD>
-FRA_DEV void split_block16(SplitLane &L, int i_base, int n, const float (&w)[16], int16_t *ring_row, bool store_ok)
+// MODE 0: exact, guarded (frame edges); 1: exact; 2: speculative (no-overflow assumption).
+template <int MODE>
+FRA_DEV float split_iterate16(SplitLane &L, int i_base, int n, const float (&w)[16], unsigned (&ob)[16])
 {
-    unsigned ob[16];
+    float absmax = 0.0f;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
         const float up_new = __shfl_up_sync(0xffffffffu, L.y, 1);   // consumed kSkew - 1 iterations from now
@@ -153,7 +156,7 @@ FRA_DEV void split_block16(SplitLane &L, int i_base, int n, const float (&w)[16]
 #pragma unroll
         for (int q = 0; q + 1 < kSkew - 1; ++q) L.up[q] = L.up[q + 1];
         L.up[kSkew - 2] = up_new;
-        if (GUARD) {
+        if (MODE == 0) {
             StageState keep = L.st;
             float ykeep = L.y;
             float y;
@@ -166,10 +169,44 @@ FRA_DEV void split_block16(SplitLane &L, int i_base, int n, const float (&w)[16]
                 L.y = ykeep;
             }
             ob[j] = __float_as_uint(acc);
+        } else if (MODE == 1) {
+            ob[j] = __float_as_uint(biquad_step(x, L.k, L.st, &L.y));
         } else {
-            float acc = biquad_step(x, L.k, L.st, &L.y);
-            ob[j] = __float_as_uint(acc);
+            ob[j] = __float_as_uint(biquad_step_spec(x, L.k, L.st, &L.y, &absmax));
         }
+    }
+    return absmax;
+}
+
+// One block of 16 iterations, then the last-stage lane's outputs go to the ring.
+// `spec_ok` (warp-uniform) selects the speculative recurrence; a block in which any
+// lane saw |y| > 32767 is rolled back and re-run exactly, and the function returns
+// true so that the caller can stop speculating on a cascade that keeps overflowing.
+template <bool GUARD>
+FRA_DEV bool split_block16(SplitLane &L, int i_base, int n, const float (&w)[16], int16_t *ring_row, bool store_ok,
+                           bool spec_ok)
+{
+    unsigned ob[16];
+    bool redone = false;
+    if (GUARD) {
+        split_iterate16<0>(L, i_base, n, w, ob);
+    } else if (spec_ok) {
+        const StageState st0 = L.st;
+        const float y0 = L.y;
+        float up0[kSkew - 1];
+#pragma unroll
+        for (int q = 0; q < kSkew - 1; ++q) up0[q] = L.up[q];
+        const float absmax = split_iterate16<2>(L, i_base, n, w, ob);
+        if (__any_sync(0xffffffffu, absmax > 32767.0f)) {
+            L.st = st0;
+            L.y = y0;
+#pragma unroll
+            for (int q = 0; q < kSkew - 1; ++q) L.up[q] = up0[q];
+            split_iterate16<1>(L, i_base, n, w, ob);
+            redone = true;
+        }
+    } else {
+        split_iterate16<1>(L, i_base, n, w, ob);
     }
     // the last-stage lane emitted samples i_base-20 .. i_base-5; with the carry
     // (i_base-24 .. i_base-21) that completes the aligned groups [i_base-24, i_base-17]
@@ -185,10 +222,13 @@ FRA_DEV void split_block16(SplitLane &L, int i_base, int n, const float (&w)[16]
     g2.w = __byte_perm(ob[10], ob[11], 0x5410);
 #pragma unroll
     for (int j = 0; j < 4; ++j) L.carry[j] = ob[12 + j];
-    if (store_ok && L.last) {
-        if (i_base >= 24 && i_base - 16 <= n) *reinterpret_cast<uint4 *>(ring_row + ((i_base - 24) & (kSplitRing - 1))) = g1;
-        if (i_base >= 16 && i_base - 8 <= n) *reinterpret_cast<uint4 *>(ring_row + ((i_base - 16) & (kSplitRing - 1))) = g2;
-    }
+    // every lane stores: lanes that are not a valid last stage own the dummy ring row,
+    // so there is no divergent branch at the block boundary.  Blocks in the interior of
+    // a frame (GUARD = false: 32 <= i_base <= n - 16) always complete both groups.
+    (void)store_ok;
+    if (!GUARD || (i_base >= 24 && i_base - 16 <= n)) *reinterpret_cast<uint4 *>(ring_row + ((i_base - 24) & (kSplitRing - 1))) = g1;
+    if (!GUARD || (i_base >= 16 && i_base - 8 <= n)) *reinterpret_cast<uint4 *>(ring_row + ((i_base - 16) & (kSplitRing - 1))) = g2;
+    return redone;
 }
 
 __global__ void __launch_bounds__(kSplitWarps * 32) k1_split(K1Args a)
@@ -287,8 +327,9 @@ __global__ void __launch_bounds__(kSplitWarps * 32) k1_split(K1Args a)
     prefetch(0);
     convert();
     const float *win_row = win + g * kSplitWinStride;
-    int16_t *ring_row = ring + g * kSplitRingStride;
+    int16_t *ring_row = ring + ((L.last && lane_valid) ? g : kSplitGroups) * kSplitRingStride;
     float wa[16], wb[16];
+    bool spec_ok = a.speculate != 0;   // warp-uniform
 
     for (int i0 = 0; i0 < a.n; i0 += kSplitChunk) {
         const bool more = (i0 + kSplitChunk) < a.n;
@@ -297,18 +338,22 @@ __global__ void __launch_bounds__(kSplitWarps * 32) k1_split(K1Args a)
         split_load_w(win_row, wa);
         if (i0 == 0) {
             split_load_w(win_row + 16, wb);
-            split_block16<true>(L, 0, a.n, wa, ring_row, lane_valid);
+            split_block16<true>(L, 0, a.n, wa, ring_row, lane_valid, false);
             split_load_w(win_row + 32, wa);
-            split_block16<true>(L, 16, a.n, wb, ring_row, lane_valid);
+            split_block16<true>(L, 16, a.n, wb, ring_row, lane_valid, false);
             b = 32;
         }
         // two blocks per trip: the samples of block b+16 are fetched while block b runs
+        int redo = 0;
         for (; b < kSplitChunk; b += 32) {
             split_load_w(win_row + b + 16, wb);
-            split_block16<false>(L, i0 + b, a.n, wa, ring_row, lane_valid);
-            if (b + 32 < kSplitChunk) split_load_w(win_row + b + 32, wa);
-            split_block16<false>(L, i0 + b + 16, a.n, wb, ring_row, lane_valid);
+            redo += split_block16<false>(L, i0 + b, a.n, wa, ring_row, lane_valid, spec_ok) ? 1 : 0;
+            split_load_w(win_row + b + 32, wa);      // past the chunk's end on the last trip: padding, never used
+            redo += split_block16<false>(L, i0 + b + 16, a.n, wb, ring_row, lane_valid, spec_ok) ? 1 : 0;
         }
+        // a cascade that keeps overflowing (16-bit wrap) gains nothing from speculation:
+        // after a chunk with more than two rolled-back blocks this warp runs exactly
+        if (redo > 2) spec_ok = false;
         __syncwarp();
         flush(i0 - 24, kSplitChunk / 8);
         __syncwarp();
@@ -317,8 +362,8 @@ __global__ void __launch_bounds__(kSplitWarps * 32) k1_split(K1Args a)
     // flush blocks: iterations n .. n+31 drain stages 1..5 and complete the groups up to [n-8, n-1]
 #pragma unroll
     for (int j = 0; j < 16; ++j) wa[j] = 0.0f;
-    split_block16<true>(L, a.n, a.n, wa, ring_row, lane_valid);
-    split_block16<true>(L, a.n + 16, a.n, wa, ring_row, lane_valid);
+    split_block16<true>(L, a.n, a.n, wa, ring_row, lane_valid, false);
+    split_block16<true>(L, a.n + 16, a.n, wa, ring_row, lane_valid, false);
     __syncwarp();
     flush(a.n - 24, 3);
 

@@ -158,33 +158,35 @@ struct BinOut {
     float qscale;
 };
 
-// one bin and its conjugate-symmetric partner: X[pos] = p/2, X[pos_conj] = conj(p)/2
+// One bin and its conjugate-symmetric partner: X[up + off] = p/2, X[dn + off_conj] = conj(p)/2.
+// `up` / `dn` are element indices (frame base +k and frame base -k) computed once per work item,
+// `off` / `off_conj` are compile-time constants, so every store is base + immediate.
 template <int QMODE>
-FRA_DEV void emit_pair(const BinOut &o, size_t frame_base, int pos, int pos_conj, bool write_conj, float2 p)
+FRA_DEV void emit_pair(const BinOut &o, size_t up, size_t dn, int off, int off_conj, bool write_conj, float2 p)
 {
     if (o.iq != nullptr) {
-        o.iq[frame_base + pos] = make_float2(0.5f * p.x, 0.5f * p.y);
-        if (write_conj) o.iq[frame_base + pos_conj] = make_float2(0.5f * p.x, -0.5f * p.y);
+        o.iq[up + off] = make_float2(0.5f * p.x, 0.5f * p.y);
+        if (write_conj) o.iq[dn + off_conj] = make_float2(0.5f * p.x, -0.5f * p.y);
     }
     if (o.frames != nullptr || o.mag != nullptr || o.phase != nullptr) {
         const float qre = quant<QMODE>(p.x, o.qscale);
         const float qim = quant<QMODE>(p.y, o.qscale);
         const float qimc = quant<QMODE>(p.y, -o.qscale);
         if (o.frames != nullptr) {
-            o.frames[frame_base + pos] = __byte_perm(__float_as_uint(qre), __float_as_uint(qim), 0x5410);
+            o.frames[up + off] = __byte_perm(__float_as_uint(qre), __float_as_uint(qim), 0x5410);
             if (write_conj)
-                o.frames[frame_base + pos_conj] = __byte_perm(__float_as_uint(qre), __float_as_uint(qimc), 0x5410);
+                o.frames[dn + off_conj] = __byte_perm(__float_as_uint(qre), __float_as_uint(qimc), 0x5410);
         }
         if (o.mag != nullptr || o.phase != nullptr) {
             const float fre = qre - kMagic, fim = qim - kMagic, fimc = qimc - kMagic;
             const float re2 = __fmul_rn(fre, fre);
             if (o.mag != nullptr) {
-                o.mag[frame_base + pos] = __fsqrt_rn(__fadd_rn(re2, __fmul_rn(fim, fim)));
-                if (write_conj) o.mag[frame_base + pos_conj] = __fsqrt_rn(__fadd_rn(re2, __fmul_rn(fimc, fimc)));
+                o.mag[up + off] = __fsqrt_rn(__fadd_rn(re2, __fmul_rn(fim, fim)));
+                if (write_conj) o.mag[dn + off_conj] = __fsqrt_rn(__fadd_rn(re2, __fmul_rn(fimc, fimc)));
             }
             if (o.phase != nullptr) {
-                o.phase[frame_base + pos] = atan2f(fim, fre);
-                if (write_conj) o.phase[frame_base + pos_conj] = atan2f(fimc, fre);
+                o.phase[up + off] = atan2f(fim, fre);
+                if (write_conj) o.phase[dn + off_conj] = atan2f(fimc, fre);
             }
         }
     }
@@ -304,71 +306,85 @@ __global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS, (LOG2N == 15) ? 1 : 2
     out.iq = (OUT == 0) ? nullptr : a.iq;
     out.mag = (OUT == 0) ? nullptr : a.mag;
     out.phase = (OUT == 0) ? nullptr : a.phase;
-#pragma unroll 1
-    for (int slot = tid; slot < P::SLOTS; slot += P::THREADS) {
-        const int fr = slot / (P::L / 2);
-        const int k0 = slot % (P::L / 2);
+
+    // one work item: the pair of sub-FFT bins (k, L-k) of frame `fr`, all F sub-sequences
+    auto item = [&](int fr, int k, float2 wn) {
         const int frame = frame0 + fr;
-        if (frame >= a.batch) continue;
-        const size_t fb = (size_t)frame * P::N;
-        const int reps = (k0 == 0) ? 2 : 1;                 // slot 0 also carries the self-paired k = L/2
-#pragma unroll 1
-        for (int rep = 0; rep < reps; ++rep) {
-            const int k = rep ? (P::L / 2) : k0;
-            const int km = (P::L - k) & (P::L - 1);
-            const float2 wn = __ldg(a.twn + k);                            // W_N^k
-            const float2 *pk = buf + fr * P::M + swz(k);                   // f L is a multiple of 8 rows
-            const float2 *pm = buf + fr * P::M + swz(km);
-            float2 za[P::F], zb[P::F];
+        const size_t up = (size_t)frame * P::N + k;
+        const size_t dn = (size_t)frame * P::N - k;
+        const int km = (P::L - k) & (P::L - 1);
+        const float2 *pk = buf + fr * P::M + swz(k);                   // f L is a multiple of 8 rows
+        const float2 *pm = buf + fr * P::M + swz(km);
+        float2 za[P::F], zb[P::F];
 #pragma unroll
-            for (int f = 0; f < P::F; ++f) {
-                za[f] = pk[f * P::L];
-                zb[f] = pm[f * P::L];
-                if (f > 0) {
-                    // W_M^(f k) = W_N^(2 f k); f = 1 by squaring W_N^k, saving a load
-                    const float2 w = (f == 1) ? make_float2(wn.x * wn.x - wn.y * wn.y, 2.0f * wn.x * wn.y)
-                                              : __ldg(a.twn + 2 * f * k);
-                    za[f] = cmul(za[f], w);
-                    // W_M^(f (L-k)) = W_F^f * conj(W_M^(f k))
-                    float2 t = cmulc(zb[f], w);
-                    if (P::F == 2) t = make_float2(-t.x, -t.y);                          // W_2^1 = -1
-                    if (P::F == 4) {
-                        if (f == 1) t = mul_mi(t);                                        // -i
-                        if (f == 2) t = make_float2(-t.x, -t.y);
-                        if (f == 3) t = make_float2(-t.y, t.x);                           // +i
-                    }
-                    if (P::F == 8) {
-                        const float h = 0.70710678118654752f;
-                        if (f == 1) t = make_float2((t.x + t.y) * h, (t.y - t.x) * h);
-                        if (f == 2) t = mul_mi(t);
-                        if (f == 3) t = make_float2((t.y - t.x) * h, -(t.x + t.y) * h);
-                        if (f == 4) t = make_float2(-t.x, -t.y);
-                        if (f == 5) t = make_float2(-(t.x + t.y) * h, (t.x - t.y) * h);
-                        if (f == 6) t = make_float2(-t.y, t.x);
-                        if (f == 7) t = make_float2((t.x - t.y) * h, (t.x + t.y) * h);
-                    }
-                    zb[f] = t;
+        for (int f = 0; f < P::F; ++f) {
+            za[f] = pk[f * P::L];
+            zb[f] = pm[f * P::L];
+            if (f > 0) {
+                // W_M^(f k) = W_N^(2 f k); f = 1 by squaring W_N^k, saving a load
+                const float2 w = (f == 1) ? make_float2(wn.x * wn.x - wn.y * wn.y, 2.0f * wn.x * wn.y)
+                                          : __ldg(a.twn + 2 * f * k);
+                za[f] = cmul(za[f], w);
+                // W_M^(f (L-k)) = W_F^f * conj(W_M^(f k))
+                float2 t = cmulc(zb[f], w);
+                if (P::F == 2) t = make_float2(-t.x, -t.y);                          // W_2^1 = -1
+                if (P::F == 4) {
+                    if (f == 1) t = mul_mi(t);                                        // -i
+                    if (f == 2) t = make_float2(-t.x, -t.y);
+                    if (f == 3) t = make_float2(-t.y, t.x);                           // +i
                 }
-            }
-            dft_small<P::F>(za);       // za[q] = Z[k + L q]
-            dft_small<P::F>(zb);       // zb[q] = Z[(L - k) + L q]
-#pragma unroll
-            for (int q = 0; q < P::F; ++q) {
-                const float2 A = za[q];
-                const float2 B = cconj(zb[P::F - 1 - q]);
-                const float2 fe = cadd(A, B);                              // 2 Fe
-                const float2 fo = mul_mi(csub(A, B));                      // 2 Fo
-                // W_N^(k + L q) = W_N^k * W_(2F)^q
-                float2 w = wn;
-                if (q > 0) w = cmul(wn, w16(q * (8 / P::F)));
-                const float2 t = cmul(w, fo);
-                const float2 p = cadd(fe, t);                              // 2 X[j]
-                const float2 m = csub(fe, t);                              // 2 X[M + j]
-                const int j = k + P::L * q;
-                emit_pair<QMODE>(out, fb, j, (P::N - j) & (P::N - 1), j != 0, p);
-                emit_pair<QMODE>(out, fb, (P::M + j) & (P::N - 1), P::M - j, true, m);
+                if (P::F == 8) {
+                    const float h = 0.70710678118654752f;
+                    if (f == 1) t = make_float2((t.x + t.y) * h, (t.y - t.x) * h);
+                    if (f == 2) t = mul_mi(t);
+                    if (f == 3) t = make_float2((t.y - t.x) * h, -(t.x + t.y) * h);
+                    if (f == 4) t = make_float2(-t.x, -t.y);
+                    if (f == 5) t = make_float2(-(t.x + t.y) * h, (t.x - t.y) * h);
+                    if (f == 6) t = make_float2(-t.y, t.x);
+                    if (f == 7) t = make_float2((t.x - t.y) * h, (t.x + t.y) * h);
+                }
+                zb[f] = t;
             }
         }
+        dft_small<P::F>(za);       // za[q] = Z[k + L q]
+        dft_small<P::F>(zb);       // zb[q] = Z[(L - k) + L q]
+#pragma unroll
+        for (int q = 0; q < P::F; ++q) {
+            const float2 A = za[q];
+            const float2 B = cconj(zb[P::F - 1 - q]);
+            const float2 fe = cadd(A, B);                              // 2 Fe
+            const float2 fo = mul_mi(csub(A, B));                      // 2 Fo
+            // W_N^(k + L q) = W_N^k * W_(2F)^q
+            float2 w = wn;
+            if (q > 0) w = cmul(wn, w16(q * (8 / P::F)));
+            const float2 t = cmul(w, fo);
+            const float2 p = cadd(fe, t);                              // 2 X[j],     j = k + L q
+            const float2 m = csub(fe, t);                              // 2 X[M + j]
+            // X[j], X[N - j] (j = 0: no partner), X[M + j], X[M - j]
+            emit_pair<QMODE>(out, up, dn, P::L * q, P::N - P::L * q, (q > 0) || (k != 0), p);
+            emit_pair<QMODE>(out, up, dn, P::M + P::L * q, P::M - P::L * q, true, m);
+        }
+    };
+
+    // k = 1 .. L/2 - 1: uniform work; the twiddle of the next item is fetched one item ahead
+    {
+        int slot = tid;
+        float2 wn_next = __ldg(a.twn + (slot % (P::L / 2)));
+#pragma unroll 1
+        for (; slot < P::SLOTS; slot += P::THREADS) {
+            const int fr = slot / (P::L / 2);
+            const int k = slot % (P::L / 2);
+            const float2 wn = wn_next;
+            const int nslot = slot + P::THREADS;
+            if (nslot < P::SLOTS) wn_next = __ldg(a.twn + (nslot % (P::L / 2)));
+            if (k != 0 && frame0 + fr < a.batch) item(fr, k, wn);
+        }
+    }
+    // the two self-paired items k = 0 and k = L/2 of every frame in the CTA
+    if (tid < 2 * P::FPC) {
+        const int fr = tid >> 1;
+        const int k = (tid & 1) ? (P::L / 2) : 0;
+        if (frame0 + fr < a.batch) item(fr, k, __ldg(a.twn + k));
     }
 }
 

@@ -57,7 +57,8 @@ def test_k1_random_coefficients_and_user_state(rom):
         coef = rng.integers(-128, 128, 12).astype(np.int8)
         if trial == 0:
             coef[:] = [-128, 127, -128, -128, 127, 0, 127, -128, 127, 127, -128, 0]
-        for flags in (_abi.FRA_K1_FORCE_LANE, _abi.FRA_K1_FORCE_SPLIT):
+        for flags in (_abi.FRA_K1_FORCE_LANE, _abi.FRA_K1_FORCE_SPLIT,
+                      _abi.FRA_K1_FORCE_SPLIT | _abi.FRA_K1_SPECULATE):      # speculation must roll back correctly
             f = EmulFra(c, n, flags)
             try:
                 f.command(bytes([0xF1]) + coef.tobytes() + bytes([0xA1]))
@@ -102,10 +103,11 @@ def test_k2_fft_all_sizes_and_framing(n, rom):
         f.close()
 
 
-def test_chain_iir_then_fft_and_host_path_agree(rom):
+@pytest.mark.parametrize("flags", [0, _abi.FRA_K1_SPECULATE])
+def test_chain_iir_then_fft_and_host_path_agree(rom, flags):
     n, c = 2048, 9
     x = g.tone_noise(range(c), n=n, seed=3)
-    f = EmulFra(c, n)
+    f = EmulFra(c, n, flags)
     try:
         f.command(bytes([0x00]))
         a = f.process(x, want=("filtered", "frames", "iq"))

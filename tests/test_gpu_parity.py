@@ -78,7 +78,8 @@ def test_k1_random_int8_coefficients_fuzz(fra, rom, seed):
     coef = rng.integers(-128, 128, 12).astype(np.int8)
     if seed == 1:
         coef[:] = [-128, 127, -128, -128, 127, 0, 127, -128, 127, 127, -128, 0]
-    for flags in (fra._abi.FRA_K1_FORCE_LANE, fra._abi.FRA_K1_FORCE_SPLIT):
+    for flags in (fra._abi.FRA_K1_FORCE_LANE, fra._abi.FRA_K1_FORCE_SPLIT,
+                  fra._abi.FRA_K1_FORCE_SPLIT | fra._abi.FRA_K1_SPECULATE):
         with fra.FraContext(c, n, flags=flags) as ctx:
             ctx.load_bank1(coef)
             ctx.set_mode(0xA1)
