@@ -31,6 +31,7 @@ FRA_ROUND_NEAREST = 0x1
 FRA_K1_FORCE_LANE = 0x2
 FRA_K1_FORCE_SPLIT = 0x4
 FRA_K1_SPECULATE = 0x8
+FRA_K1_FORCE_STAGE = 0x10
 
 
 class FraOutputs(C.Structure):

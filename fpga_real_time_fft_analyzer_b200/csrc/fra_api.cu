@@ -183,10 +183,18 @@ int process_range(fra_ctx *ctx, const int16_t *d_in, int c0, int nch, int contin
         k1.continuous = continuous;
         k1.speculate = (ctx->flags & FRA_K1_SPECULATE) ? 1 : 0;
         if (ctx->profiling) FRA_TRY(ctx, cudaEventRecord(ctx->ev[0], st));
-        bool split = nch < kLaneMinChannels;
-        if (ctx->flags & FRA_K1_FORCE_LANE) split = false;
-        if (ctx->flags & FRA_K1_FORCE_SPLIT) split = true;
-        if (split) {
+        // k1_lane needs ~19k channels to fill 592 schedulers; below that the stage-per-warp
+        // pipeline; the stage-per-lane systolic kernel only on request (and for one stream)
+        int variant = (nch < kLaneMinChannels) ? 2 : 0;          // 0 lane, 1 split, 2 stage
+        if (ctx->flags & FRA_K1_FORCE_LANE) variant = 0;
+        if (ctx->flags & FRA_K1_FORCE_SPLIT) variant = 1;
+        if (ctx->flags & FRA_K1_FORCE_STAGE) variant = 2;
+        if (variant == 2) {
+            const int grid = (nch + 31) / 32;
+            auto kfn = k1_stage;
+            FRA_TRY(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageSmemBytes));
+            FRA_LAUNCH(kfn, dim3(grid), dim3(kStageWarps * 32), (size_t)kStageSmemBytes, st, k1);
+        } else if (variant == 1) {
             const int per_cta = kSplitWarps * kSplitGroups;
             const int grid = (nch + per_cta - 1) / per_cta;
             const size_t smem = (size_t)kSplitWarps * kSplitSmemPerWarp;

@@ -113,6 +113,9 @@ FRA_DEV int window_int(int x, int c)
     return v == 32768 ? 0 : v;
 }
 
+// the same without the resize quirk: valid whenever c != -32768 (all but 30 ROM entries)
+FRA_DEV int window_int_fast(int x, int c) { return (x * c + 16384) >> 15; }
+
 // int in [-32768, 32767] -> float without the conversion pipe
 FRA_DEV float small_int_to_float(int v)
 {
@@ -171,6 +174,22 @@ FRA_DEV void mbar_wait(uint64_t *bar, unsigned parity)
 }
 // orders this thread's generic-proxy shared-memory accesses before later async-proxy (bulk copy) writes
 FRA_DEV void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#endif
+
+// ---- per-thread asynchronous 16-byte global -> shared copies (cp.async, SASS LDGSTS).
+// Unlike a register prefetch they occupy no scoreboard slot, so a later wait on an OLDER
+// load can never be held up by them (B200: six counting scoreboards per warp, shared).
+#ifdef FRA_HOST_EMUL
+FRA_DEV void cp_async16(void *dst, const void *src) { std::memcpy(dst, src, 16); }
+FRA_DEV void cp_async_commit() {}
+template <int N> FRA_DEV void cp_async_wait() {}
+#else
+FRA_DEV void cp_async16(void *dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+FRA_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> FRA_DEV void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 #endif
 
 FRA_DEV uint4 ldg128(const void *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }

@@ -31,7 +31,7 @@ int main()
     // 2. low-16-bit wrap of the offset-binary accumulator -> float, for every reachable sum
     for (int s = -5 * 32768 - 8; s <= 5 * 32768 + 8; ++s) {
         float acc = kMagicB + (float)s;
-        float y = wrap16_to_float(acc);
+        float y = wrap16_to_float(acc, 0x4B000000u);
         int want = (int)(short)(unsigned short)(s & 0xFFFF);
         if (y != (float)want) { if (bad < 10) std::printf("wrap mismatch s=%d y=%f want=%d\n", s, y, want); ++bad; }
         if ((int)(short)acc_to_u16(acc) != want) { ++bad; }

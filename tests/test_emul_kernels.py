@@ -23,8 +23,9 @@ def adversarial(rng, c, n):
     return x
 
 
-@pytest.mark.parametrize("flags,name", [(_abi.FRA_K1_FORCE_LANE, "lane"), (_abi.FRA_K1_FORCE_SPLIT, "split")])
-@pytest.mark.parametrize("channels", [1, 6, 23])
+@pytest.mark.parametrize("flags,name", [(_abi.FRA_K1_FORCE_LANE, "lane"), (_abi.FRA_K1_FORCE_SPLIT, "split"),
+                                        (_abi.FRA_K1_FORCE_STAGE, "stage")])
+@pytest.mark.parametrize("channels", [1, 6, 37])
 def test_k1_bit_exact_with_state_and_reload(flags, name, channels, rom):
     rng = np.random.default_rng(channels)
     n = 1024
@@ -57,7 +58,7 @@ def test_k1_random_coefficients_and_user_state(rom):
         coef = rng.integers(-128, 128, 12).astype(np.int8)
         if trial == 0:
             coef[:] = [-128, 127, -128, -128, 127, 0, 127, -128, 127, 127, -128, 0]
-        for flags in (_abi.FRA_K1_FORCE_LANE, _abi.FRA_K1_FORCE_SPLIT,
+        for flags in (_abi.FRA_K1_FORCE_LANE, _abi.FRA_K1_FORCE_SPLIT, _abi.FRA_K1_FORCE_STAGE,
                       _abi.FRA_K1_FORCE_SPLIT | _abi.FRA_K1_SPECULATE):      # speculation must roll back correctly
             f = EmulFra(c, n, flags)
             try:
