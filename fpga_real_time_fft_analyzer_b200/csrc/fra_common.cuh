@@ -70,10 +70,13 @@ FRA_DEV unsigned acc_to_u16(float acc) { return (__float_as_uint(acc) ^ 0x8000u)
 // Returns the accumulator; *y_out gets the wrapped value as a float.  Every partial
 // sum is an exact integer, so the order of the five terms is free: the ones that
 // are known early go first.
+// B1Z: the x[n-1] coefficient is zero in both sets (true of the reference's fixed bank,
+// IMP/filter_pkg.vhd:58,67): T(v, 0) = 0 exactly, so that product is skipped.
+template <bool B1Z = false>
 FRA_DEV float biquad_step(float x, const StageCoef &k, StageState &s, float *y_out)
 {
     float acc = __fmaf_rd(s.x2, k.b0, kMagicB);
-    acc = __fmaf_rd(s.x1, k.b1, acc);
+    if (!B1Z) acc = __fmaf_rd(s.x1, k.b1, acc);
     acc = __fmaf_ru(s.y2, k.na0, acc);
     acc = __fmaf_rd(x, k.b2, acc);          // x arrives late (previous stage / shuffle): fourth
     acc = __fmaf_ru(s.y1, k.na1, acc);      // y[n-1] is the recurrence: last

@@ -38,6 +38,7 @@ struct K1Args {
 // ------------------------------------------------------------------ k1_lane
 constexpr int kLaneBlock = 32;       // one warp per CTA: 2048 warps spread evenly over 148 SMs x 4 schedulers
 
+template <bool B1Z>
 __global__ void __launch_bounds__(kLaneBlock) k1_lane(K1Args a)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -83,7 +84,7 @@ __global__ void __launch_bounds__(kLaneBlock) k1_lane(K1Args a)
                 float v = small_int_to_float(window_int(x, rom[j]));
 #pragma unroll
                 for (int s = 0; s < kStages; ++s)
-                    acc[j] = biquad_step(v, a.coef.set[s & 1], st[s], &v);
+                    acc[j] = biquad_step<B1Z>(v, a.coef.set[s & 1], st[s], &v);
             }
             ow[2 * q] = pack16_acc(acc[0], acc[1]);
             ow[2 * q + 1] = pack16_acc(acc[2], acc[3]);
@@ -466,17 +467,17 @@ FRA_DEV void stage_loader_step(const int16_t *src, const int *rom32, int t, int 
 }
 
 // 16 samples of one stage: four float4 in, four float4 (or 32 packed bytes) out
-template <bool LAST>
+template <bool LAST, bool B1Z>
 FRA_DEV void stage_group16(const float4 (&in)[4], const StageCoef &k, StageState &st, float4 *tout, int16_t *gout,
                            bool live)
 {
     float acc[16], y[16];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        acc[4 * q + 0] = biquad_step(in[q].x, k, st, &y[4 * q + 0]);
-        acc[4 * q + 1] = biquad_step(in[q].y, k, st, &y[4 * q + 1]);
-        acc[4 * q + 2] = biquad_step(in[q].z, k, st, &y[4 * q + 2]);
-        acc[4 * q + 3] = biquad_step(in[q].w, k, st, &y[4 * q + 3]);
+        acc[4 * q + 0] = biquad_step<B1Z>(in[q].x, k, st, &y[4 * q + 0]);
+        acc[4 * q + 1] = biquad_step<B1Z>(in[q].y, k, st, &y[4 * q + 1]);
+        acc[4 * q + 2] = biquad_step<B1Z>(in[q].z, k, st, &y[4 * q + 2]);
+        acc[4 * q + 3] = biquad_step<B1Z>(in[q].w, k, st, &y[4 * q + 3]);
     }
     if (!LAST) {
 #pragma unroll
@@ -494,7 +495,7 @@ FRA_DEV void stage_group16(const float4 (&in)[4], const StageCoef &k, StageState
 
 // one chunk (64 samples) of one stage, straight-line: inputs of group g+1 are in flight
 // while group g is filtered, and nothing is copied between iterations
-template <bool LAST>
+template <bool LAST, bool B1Z>
 FRA_DEV void stage_chunk(const float4 *tin, float4 *tout, int16_t *gout, const StageCoef &k, StageState &st, bool live)
 {
     float4 buf[2][4];
@@ -506,10 +507,11 @@ FRA_DEV void stage_chunk(const float4 *tin, float4 *tout, int16_t *gout, const S
 #pragma unroll
             for (int q = 0; q < 4; ++q) buf[(g + 1) & 1][q] = tin[((g + 1) * 4 + q) * 32];
         }
-        stage_group16<LAST>(buf[g & 1], k, st, tout + (g * 4) * 32, gout + 16 * g, live);
+        stage_group16<LAST, B1Z>(buf[g & 1], k, st, tout + (g * 4) * 32, gout + 16 * g, live);
     }
 }
 
+template <bool B1Z>
 __global__ void __launch_bounds__(kStageWarps * 32, 2) k1_stage(K1Args a)
 {
     FRA_DYN_SMEM(smem_raw);
@@ -551,9 +553,9 @@ __global__ void __launch_bounds__(kStageWarps * 32, 2) k1_stage(K1Args a)
             if (chunk >= 0 && chunk < n_chunks) {
                 const float4 *tin = stage_tile(smem, s, chunk & 1) + lane;
                 if (s + 1 < kStages) {
-                    stage_chunk<false>(tin, stage_tile(smem, s + 1, chunk & 1) + lane, nullptr, k, st, live);
+                    stage_chunk<false, B1Z>(tin, stage_tile(smem, s + 1, chunk & 1) + lane, nullptr, k, st, live);
                 } else {
-                    stage_chunk<true>(tin, nullptr, dst + (size_t)chunk * kStageChunk, k, st, live);
+                    stage_chunk<true, B1Z>(tin, nullptr, dst + (size_t)chunk * kStageChunk, k, st, live);
                 }
             }
             __syncthreads();
