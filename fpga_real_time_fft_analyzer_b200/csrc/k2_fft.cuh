@@ -211,7 +211,7 @@ FRA_DEV float2 w16(int q)
 // OUT = 0: int16 frames only (the hot configuration); OUT = 1: any combination of
 // outputs, selected at run time by the null pointers in K2Args.
 template <int LOG2N, bool WIN, int QMODE, int OUT>
-__global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS, (LOG2N == 15) ? 1 : 2) k2_fft(K2Args a)
+__global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS, (LOG2N == 15) ? 1 : 3) k2_fft(K2Args a)
 {
     using P = FftPlan<LOG2N>;
     constexpr int IPT = P::ITEMS / P::THREADS;          // butterflies per thread per pass (2)
