@@ -41,8 +41,9 @@ constexpr int kLaneBlock = 32;       // one warp per CTA: 2048 warps spread even
 template <bool B1Z>
 __global__ void __launch_bounds__(kLaneBlock) k1_lane(K1Args a)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= a.channels) return;
+    const int c_raw = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = c_raw < a.channels;
+    const int c = live ? c_raw : a.channels - 1;     // inactive lanes shadow the last channel (no stores)
 
     StageState st[kStages];
     {
@@ -60,22 +61,32 @@ __global__ void __launch_bounds__(kLaneBlock) k1_lane(K1Args a)
     const int16_t *src = a.in + (size_t)c * a.n;
     int16_t *dst = a.out + (size_t)c * a.n;
 
-    // software prefetch: the next 16 samples are requested before the current 16 are filtered
-    uint4 xa = ldg128(src), xb = ldg128(src + 8);
-    for (int n0 = 0; n0 < a.n; n0 += 16) {
+    // The next 16 samples (and their 16 window ROM entries) are requested one trip ahead by
+    // cp.async into shared memory: a register prefetch would share one of the warp's six
+    // scoreboards with the trip's other loads and stall on them (measured).
+    __shared__ uint4 stage_x[2][2][kLaneBlock];      // [buffer][half][lane]: 16 samples per lane
+    __shared__ int4 stage_rom[2][4];                 // [buffer][4 x 4 ROM entries]
+    const int lane = threadIdx.x;
+    auto request = [&](int n0, int b) {
+        cp_async16(&stage_x[b][0][lane], src + n0);
+        cp_async16(&stage_x[b][1][lane], src + n0 + 8);
+        if (lane < 4) cp_async16(&stage_rom[b][lane], a.rom32 + ((n0 + 4 * lane) & (kWindowLen - 1)));
+        cp_async_commit();
+    };
+    request(0, 0);
+    for (int n0 = 0, it = 0; n0 < a.n; n0 += 16, ++it) {
+        const int b = it & 1;
+        if (n0 + 16 < a.n) request(n0 + 16, b ^ 1);
+        else cp_async_commit();
+        cp_async_wait<1>();
+        __syncwarp();                                 // the ROM words were copied by lanes 0..3
+        const uint4 xa = stage_x[b][0][lane], xb = stage_x[b][1][lane];
         const unsigned xw[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
-        if (n0 + 16 < a.n) {
-            xa = ldg128(src + n0 + 16);
-            xb = ldg128(src + n0 + 24);
-        }
-        const int4 *rp = reinterpret_cast<const int4 *>(a.rom32 + (n0 & (kWindowLen - 1)));
-        int4 rr[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) rr[q] = __ldg(rp + q);   // warp-uniform address: one L1 broadcast each
         unsigned ow[8];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const int rom[4] = {rr[q].x, rr[q].y, rr[q].z, rr[q].w};
+            const int4 r = stage_rom[b][q];           // same address in every lane: broadcast
+            const int rom[4] = {r.x, r.y, r.z, r.w};
             float acc[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -89,11 +100,14 @@ __global__ void __launch_bounds__(kLaneBlock) k1_lane(K1Args a)
             ow[2 * q] = pack16_acc(acc[0], acc[1]);
             ow[2 * q + 1] = pack16_acc(acc[2], acc[3]);
         }
-        stg128(dst + n0, make_uint4(ow[0], ow[1], ow[2], ow[3]));
-        stg128(dst + n0 + 8, make_uint4(ow[4], ow[5], ow[6], ow[7]));
+        if (live) {
+            stg128(dst + n0, make_uint4(ow[0], ow[1], ow[2], ow[3]));
+            stg128(dst + n0 + 8, make_uint4(ow[4], ow[5], ow[6], ow[7]));
+        }
+        __syncwarp();                                 // everyone has read buffer b before it is refilled
     }
 
-    {
+    if (live) {
         uint2 *sp = reinterpret_cast<uint2 *>(a.state + (size_t)c * 24);
 #pragma unroll
         for (int s = 0; s < kStages; ++s) {
