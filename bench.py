@@ -26,6 +26,8 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: NCCL's own banner / debug output goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 CHANNELS = 4096
 N = 16384
@@ -261,7 +263,7 @@ def run_ours(args):
                 kernels[name] = {"ms": ms, "achieved_gbs": ach, "frac": ach / peak,
                                  "alg_bytes_per_sample": B_ALG[name]}
         dom = "window_iir" if k1 >= k2 else "fft_pack"
-        roofline = {"bound": "hbm", "kernel": ("k1_split" if dom == "window_iir" else "k2_fft<14,false,0>"),
+        roofline = {"bound": "hbm", "kernel": ("k1_stage<true>" if dom == "window_iir" else "k2_fft<14,false,0,0>"),
                     "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                     "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
                     "kernels": kernels,
