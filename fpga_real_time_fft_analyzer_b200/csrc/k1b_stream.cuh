@@ -7,20 +7,31 @@
 // evaluation therefore cannot be bit-exact; K1b is the chunked scan with that
 // stated error, and the bit-exact answer for one stream is the systolic k1_split
 // kernel with one channel (fra_iir_stream(exact = 1)).
-//   1. speculate  one lane per chunk: start `warm` samples before the chunk from
-//                 a zero history and run the exact cascade up to the chunk start.
-//                 The linear part of the missing history is A^warm * s, below half
-//                 an LSB once warm >= 18 ln2 / -ln(pole radius): the block scan of
-//                 the state-space recurrence truncated to its nearest neighbour,
-//                 which is all that survives for a stable cascade.  Then filter
-//                 the chunk; record entry and exit states;
-//   2. verify     neighbouring chunks compare exit(p-1) with entry(p) - the
-//                 neighbour's state travels one lane up by warp shuffle - and
-//                 report how many differ and by how many LSB at most.
+//
+// The scan is a block scan of the cascade's STATE-SPACE recurrence.  The affine
+// model of one sample step,  s' = A s + B u + d  (s = the 24 history values of the
+// six stages, u = the windowed sample, d = the mean truncation offset -1/2 per
+// non-zero product), gives over a chunk of L samples  s(end) = A^L s(begin) + e,
+// with e the zero-state response of the chunk:
+//   1. k1b_lin_ends    one lane per chunk: e_p, by running the float model over the chunk
+//   2. k1b_scan_warp   inside each warp a Hillis-Steele scan by __shfl_up with the powers
+//                      (A^L)^1,2,4,8,16 (24x24, from the host, in shared memory);
+//      k1b_scan_carry  the warps' aggregates chained with (A^L)^32;
+//      k1b_scan_warp   again, with each warp's carry injected: the state at every chunk
+//                      boundary
+//   3. k1b_speculate   one lane per chunk: start from the rounded predicted state, filter
+//                      the chunk with the EXACT integer cascade, record the exit state
+//   4. k1b_verify      neighbours compare exit(p-1) with entry(p) - the neighbour's state
+//                      travels one lane up by warp shuffle - and report how many differ
+//                      and by how many LSB at most.
 #pragma once
 #include "fra_common.cuh"
 
 namespace fra {
+
+constexpr int kStateDim = 4 * kStages;      // (x1, x2, y1, y2) x 6 stages
+constexpr int kScanLevels = 5;              // lane distances 1, 2, 4, 8, 16
+constexpr int kScanMats = kScanLevels + 1;  // + (A^L)^32 for the carry across warps
 
 struct K1bArgs {
     const int16_t *in;      // [n]
@@ -31,10 +42,13 @@ struct K1bArgs {
     int16_t *exit_;         // [P][24] state after each chunk's last sample
     const int16_t *state0;  // [24] true state before sample 0 (used when continuous)
     int *stats;             // [0] chunks whose entry state differs from the neighbour's exit, [1] max |difference| (LSB)
+    float *ends;            // [P][24] zero-state responses e_p, then predicted states s_p (in place)
+    float *aggr;            // [2][ceil(P/32)][24]: per-warp aggregates G_w, then carries C_w
+    const float *mats;      // [6][24][24] (A^L)^(1,2,4,8,16,32), row-major
     unsigned long long n;   // samples
-    int chunk;              // samples per chunk (multiple of 8)
-    int warm;               // warm-up samples
+    int chunk;              // samples per chunk L (multiple of 8)
     int n_chunks;
+    int n_warps;            // ceil(n_chunks / 32)
     int continuous;
     int apply_window;
     int iir;                // 0: bypass (window only)
@@ -68,10 +82,33 @@ FRA_DEV void state_zero(StageState (&st)[kStages])
     for (int s = 0; s < kStages; ++s) st[s].x1 = st[s].x2 = st[s].y1 = st[s].y2 = 0.0f;
 }
 
-// run samples [begin, end) (multiples of 8) of the stream through window + cascade
-template <bool WRITE>
+// the affine float model of one biquad step: products are not truncated, each non-zero
+// product carries the mean of its truncation (-1/2 LSB; +1/2 for the subtracted terms)
+FRA_DEV float biquad_linear(float x, const StageCoef &k, StageState &s, float bias)
+{
+    float y = bias;
+    y = fmaf(s.x2, k.b0, y);
+    y = fmaf(s.x1, k.b1, y);
+    y = fmaf(s.y2, k.na0, y);
+    y = fmaf(x, k.b2, y);
+    y = fmaf(s.y1, k.na1, y);
+    s.x2 = s.x1; s.x1 = x;
+    s.y2 = s.y1; s.y1 = y;
+    return y;
+}
+
+FRA_DEV float stage_bias(const StageCoef &k)
+{
+    // floor() lowers each added product by 1/2 on average and raises each subtracted one
+    return -0.5f * ((k.b0 != 0.0f) + (k.b1 != 0.0f) + (k.b2 != 0.0f)) + 0.5f * ((k.na0 != 0.0f) + (k.na1 != 0.0f));
+}
+
+// samples [begin, end) (multiples of 8) through window + cascade.
+// MODE 0: exact, no output; 1: exact, write output; 2: float model, no output
+template <int MODE>
 FRA_DEV void stream_run(const K1bArgs &a, StageState (&st)[kStages], unsigned long long begin, unsigned long long end)
 {
+    const float bias0 = stage_bias(a.coef.set[0]), bias1 = stage_bias(a.coef.set[1]);
     for (unsigned long long n0 = begin; n0 < end; n0 += 8) {
         const uint4 xv = ldg128(a.in + n0);
         const unsigned xw[4] = {xv.x, xv.y, xv.z, xv.w};
@@ -87,35 +124,162 @@ FRA_DEV void stream_run(const K1bArgs &a, StageState (&st)[kStages], unsigned lo
                 float v = small_int_to_float(x);
                 float acc = __int_as_float((x + 32768) + 0x4B400000);     // offset-binary, as biquad_step leaves it
                 if (a.iir) {
+                    if (MODE == 2) {
 #pragma unroll
-                    for (int s = 0; s < kStages; ++s) acc = biquad_step(v, a.coef.set[s & 1], st[s], &v);
+                        for (int s = 0; s < kStages; ++s) v = biquad_linear(v, a.coef.set[s & 1], st[s], (s & 1) ? bias1 : bias0);
+                    } else {
+#pragma unroll
+                        for (int s = 0; s < kStages; ++s) acc = biquad_step(v, a.coef.set[s & 1], st[s], &v);
+                    }
                 }
                 acc2[e] = acc;
             }
             ow[h] = pack16_acc(acc2[0], acc2[1]);
         }
-        if (WRITE) stg128(a.out + n0, make_uint4(ow[0], ow[1], ow[2], ow[3]));
+        if (MODE == 1) stg128(a.out + n0, make_uint4(ow[0], ow[1], ow[2], ow[3]));
     }
 }
 
+// the scan is over the chunk boundaries b_p = p L: segment p is [b_p, b_{p+1})
+FRA_DEV unsigned long long scan_boundary(const K1bArgs &a, int p)
+{
+    unsigned long long b = (unsigned long long)p * (unsigned long long)a.chunk;
+    return b < a.n ? b : a.n;
+}
+
+// 1. zero-state response of segment p in the float model
+__global__ void __launch_bounds__(64) k1b_lin_ends(K1bArgs a)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.n_chunks) return;
+    StageState st[kStages];
+    state_zero(st);
+    stream_run<2>(a, st, scan_boundary(a, p), scan_boundary(a, p + 1));
+    float *e = a.ends + (size_t)p * kStateDim;
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) {
+        e[4 * s + 0] = st[s].x1; e[4 * s + 1] = st[s].x2; e[4 * s + 2] = st[s].y1; e[4 * s + 3] = st[s].y2;
+    }
+}
+
+// 2. Hillis-Steele scan of  s_{p+1} = M s_p + e_p  (M = A^L) inside one warp: 32 boundaries,
+// the neighbour's partial sum arriving by __shfl_up, M^(2^j) broadcast from shared memory.
+// With a_0 = s_0 and a_p = e_{p-1}:  s_p = sum_{q <= p} M^(p-q) a_q.  Lane i of warp w ends up
+// with the sum over q = 32 w .. 32 w + i.  PHASE 0 (no carry) keeps only the warp's aggregate
+// G_w (lane 31); PHASE 1 first adds the carry C_w = M s_{32 w - 1} at lane 0, so that every
+// lane holds the full state s_p, and writes it, rounded, as chunk p's predicted entry state.
+template <int PHASE>
+__global__ void __launch_bounds__(32) k1b_scan_warp(K1bArgs a)
+{
+    __shared__ float sm[kScanLevels][kStateDim * kStateDim];
+    const int lane = threadIdx.x;
+    const int w = blockIdx.x;
+    for (int i = lane; i < kScanLevels * kStateDim * kStateDim; i += 32) (&sm[0][0])[i] = __ldg(a.mats + i);
+    __syncwarp();
+    const int p = 32 * w + lane;
+    const bool live = p < a.n_chunks;
+    float v[kStateDim];
+#pragma unroll
+    for (int i = 0; i < kStateDim; ++i) v[i] = 0.0f;
+    if (live && p > 0) {
+        const float *e = a.ends + (size_t)(p - 1) * kStateDim;
+#pragma unroll
+        for (int i = 0; i < kStateDim; ++i) v[i] = e[i];
+    }
+    if (lane == 0) {
+        if (w == 0) {
+            if (a.continuous) {
+#pragma unroll
+                for (int i = 0; i < kStateDim; ++i) v[i] = (float)a.state0[i];     // the true state before sample 0
+            }
+        } else if (PHASE == 1) {
+            const float *c = a.aggr + (size_t)(a.n_warps + w) * kStateDim;
+#pragma unroll
+            for (int i = 0; i < kStateDim; ++i) v[i] += c[i];
+        }
+    }
+#pragma unroll 1
+    for (int lvl = 0; lvl < kScanLevels; ++lvl) {
+        const int d = 1 << lvl;
+        float t[kStateDim];
+#pragma unroll
+        for (int i = 0; i < kStateDim; ++i) t[i] = __shfl_up_sync(0xffffffffu, v[i], d);
+        if (lane >= d) {
+            const float *m = sm[lvl];
+#pragma unroll
+            for (int r = 0; r < kStateDim; ++r) {
+                float acc = v[r];
+#pragma unroll
+                for (int c = 0; c < kStateDim; ++c) acc = fmaf(m[r * kStateDim + c], t[c], acc);
+                v[r] = acc;
+            }
+        }
+    }
+    if (PHASE == 0) {
+        if (lane == 31) {                              // only full warps hand an aggregate on
+            float *g = a.aggr + (size_t)w * kStateDim;
+#pragma unroll
+            for (int i = 0; i < kStateDim; ++i) g[i] = v[i];
+        }
+    } else if (live && p > 0) {
+        int16_t *o = a.entry + (size_t)p * kStateDim;
+#pragma unroll
+        for (int i = 0; i < kStateDim; ++i) {
+            const float r = fminf(fmaxf(rintf(v[i]), -32768.0f), 32767.0f);
+            o[i] = (int16_t)(int)r;
+        }
+    }
+}
+
+// the warps' aggregates chained, one warp, one state row per lane:
+//   S_w = G_w + M^32 S_{w-1}   (S_w = state at boundary 32 w + 31),   C_{w+1} = M S_w
+__global__ void __launch_bounds__(32) k1b_scan_carry(K1bArgs a)
+{
+    __shared__ float m1[kStateDim * kStateDim], m32[kStateDim * kStateDim], cur[kStateDim], nxt[kStateDim];
+    const int lane = threadIdx.x;
+    for (int i = lane; i < kStateDim * kStateDim; i += 32) {
+        m1[i] = __ldg(a.mats + i);
+        m32[i] = __ldg(a.mats + kScanLevels * kStateDim * kStateDim + i);
+    }
+    if (lane < kStateDim) cur[lane] = 0.0f;
+    __syncwarp();
+    for (int w = 0; w + 1 < a.n_warps; ++w) {
+        if (lane < kStateDim) {
+            float acc = a.aggr[(size_t)w * kStateDim + lane];
+            if (w > 0)
+                for (int c = 0; c < kStateDim; ++c) acc = fmaf(m32[lane * kStateDim + c], cur[c], acc);
+            nxt[lane] = acc;
+        }
+        __syncwarp();
+        if (lane < kStateDim) cur[lane] = nxt[lane];
+        __syncwarp();
+        if (lane < kStateDim) {
+            float acc = 0.0f;
+            for (int c = 0; c < kStateDim; ++c) acc = fmaf(m1[lane * kStateDim + c], cur[c], acc);
+            a.aggr[(size_t)(a.n_warps + w + 1) * kStateDim + lane] = acc;
+        }
+        __syncwarp();
+    }
+}
+
+// 3. exact filtering of chunk p from the scan's predicted state (chunk 0: the true state)
 __global__ void __launch_bounds__(64) k1b_speculate(K1bArgs a)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= a.n_chunks) return;
-    const unsigned long long start = (unsigned long long)p * (unsigned long long)a.chunk;
-    unsigned long long end = start + (unsigned long long)a.chunk;
-    if (end > a.n) end = a.n;
-    const unsigned long long w0 = (start > (unsigned long long)a.warm) ? start - (unsigned long long)a.warm : 0ull;
     StageState st[kStages];
-    if (w0 == 0 && a.continuous) state_load(st, a.state0);
-    else state_zero(st);
-    stream_run<false>(a, st, w0, start);
-    state_store(st, a.entry + (size_t)p * 24);
-    stream_run<true>(a, st, start, end);
-    state_store(st, a.exit_ + (size_t)p * 24);
+    if (p == 0) {
+        if (a.continuous) state_load(st, a.state0);
+        else state_zero(st);
+        state_store(st, a.entry);
+    } else {
+        state_load(st, a.entry + (size_t)p * kStateDim);
+    }
+    stream_run<1>(a, st, scan_boundary(a, p), scan_boundary(a, p + 1));
+    state_store(st, a.exit_ + (size_t)p * kStateDim);
 }
 
-// verify: lane p compares its entry state with lane p-1's exit state; the exit
+// 4. verify: lane p compares its entry state with lane p-1's exit state; the exit
 // state moves one lane up by shuffle (the warp's first lane reads it from memory)
 FRA_DEV int absdiff16(unsigned a, unsigned b)
 {

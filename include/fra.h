@@ -138,21 +138,23 @@ int fra_set_state(fra_ctx *ctx, const int16_t *d_state, void *cuda_stream);
  * currently selected mode.
  *   exact != 0  bit-exact: the six stages run as a systolic chain on six warp lanes
  *               (the stage-per-lane kernel with one channel); n must be a multiple of 256.
- *   exact == 0  time-parallel chunked scan: one lane per chunk, each chunk's entry
- *               state predicted by a warm-up run whose length is set from the pole
- *               radius, neighbours verified by warp shuffles.  Because every product
- *               is truncated (NEW/filter_iir_cust.vhd:96-100) the cascade is not linear
- *               and this path is NOT bit-exact: it settles within the dead band of the
- *               truncating sections, a few LSB from the serial result; `stats` reports
- *               how many chunk boundaries differ and by how many LSB.  n multiple of 8.
- *               Falls back to the exact path when the poles are too close to the unit
- *               circle for a bounded warm-up (stats->exact is set).
+ *   exact == 0  time-parallel chunked scan: one lane per 4096-sample chunk; each chunk's
+ *               entry state comes from a block scan of the cascade's state-space
+ *               recurrence (float model, 24 x 24 chunk-transition powers combined by warp
+ *               shuffles); the chunks are then filtered exactly from those states and
+ *               neighbours verified by warp shuffles.  Because every product is truncated
+ *               (NEW/filter_iir_cust.vhd:96-100) the cascade is not linear and this path
+ *               is NOT bit-exact: it stays within the dead band of the truncating
+ *               sections, a few LSB from the serial result; `stats` reports how many
+ *               chunk boundaries differ and by how many LSB.  n multiple of 8.  Falls
+ *               back to the exact path when the poles are too close to the unit circle
+ *               or the deviation shows an overflowing (wrapping) cascade (stats->exact).
  * Synchronous. */
 typedef struct fra_stream_stats {
     int exact;          /* 1 if the exact path produced the output */
     int n_chunks;
     int chunk;          /* samples per chunk */
-    int warmup;         /* warm-up samples per chunk */
+    int warmup;         /* exact warm-up samples per chunk (0: the block scan predicts the entry states) */
     int n_mismatch;     /* chunk boundaries whose predicted entry state != neighbour's exit state */
     int max_state_dev;  /* largest such difference, LSB */
 } fra_stream_stats;

@@ -199,8 +199,8 @@ def test_stream_exact_and_chunked_modes(rom):
         y, stats = f.iir_stream(x[:4096], exact=True)                # six-lane systolic chain: bit-exact
         assert stats["exact"] == 1 and np.array_equal(y, yr[0, :4096])
         y, stats = f.iir_stream(x, exact=False)                       # chunked scan: dead-band error only
-        assert stats["exact"] == 0 and stats["n_chunks"] > 1 and stats["warmup"] >= 256
-        assert stats["max_state_dev"] <= 32
+        assert stats["exact"] == 0 and stats["n_chunks"] == 16 and stats["chunk"] == 4096
+        assert 0 < stats["max_state_dev"] <= 32           # block-scan prediction: inside the dead band, not exact
         assert np.abs(y.astype(int) - yr[0].astype(int)).max() <= 64
         first = stats["chunk"]
         assert np.array_equal(y[:first], yr[0, :first])               # chunk 0 starts from the true state

@@ -1,0 +1,42 @@
+#!/usr/bin/env python3
+"""BASELINE config 5 timings: one long stream through K1b (exact systolic chain vs block scan)
+and the FFT alone at N = 1K .. 32K with batch = 2^26 / N samples."""
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from fpga_real_time_fft_analyzer_b200 import FraContext, synth  # noqa: E402
+
+dev = "cuda"
+n = 1 << 24
+x = synth.tone_noise(1, n, dev)[0].contiguous()
+with FraContext(1, 16384) as ctx:
+    ctx.command(0x00)
+    for exact in (False, True):
+        ctx.iir_stream(x[: 1 << 20], exact=exact)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        y, st = ctx.iir_stream(x, exact=exact)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        print(f"stream 2^24 samples exact={int(exact)}: {dt * 1e3:.2f} ms  {n / dt / 1e9:.3f} Gsamples/s  stats={st}")
+for log2n in range(10, 16):
+    N = 1 << log2n
+    batch = (1 << 26) // N
+    with FraContext(batch, N) as ctx:
+        xs = synth.full_range(batch, N, dev)
+        ctx.fft_only(xs)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(5):
+            out = ctx.fft_only(xs)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        print(f"fft_only N={N:6d} batch={batch:6d}: {ms:.4f} ms  {batch * N / ms / 1e6:.1f} Gsamples/s (int16 in, complex64 out: "
+              f"{batch * N * 10 / ms / 1e6:.0f} GB/s)")
+print("64K: not supported (needs 256 KiB of shared memory: 2-CTA cluster + DSMEM, see DESIGN.md)")
