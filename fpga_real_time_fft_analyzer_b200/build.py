@@ -31,7 +31,7 @@ def build(force=False, verbose=False):
     if not force and not stale():
         return OUT
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-           "-shared", "-Xcompiler", "-fPIC", "--cudart", "static", "-o", OUT, SRC]
+           "-DFRA_USE_F32X2", "-shared", "-Xcompiler", "-fPIC", "--cudart", "static", "-o", OUT, SRC]
     if verbose:
         cmd[1:1] = ["-Xptxas", "-v"]
     subprocess.check_call(cmd)
