@@ -32,6 +32,7 @@ FRA_K1_FORCE_LANE = 0x2
 FRA_K1_FORCE_SPLIT = 0x4
 FRA_K1_SPECULATE = 0x8
 FRA_K1_FORCE_STAGE = 0x10
+FRA_K1_FORCE_DUO = 0x20
 
 
 class FraOutputs(C.Structure):

@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -98,6 +99,7 @@ StageCoef make_stage(const int8_t *k)       // k = B0,B1,B2,A0,A1 (NEW/filter_ii
     c.na0 = -(float)k[3] / 128.0f;
     c.na1 = -(float)k[4] / 128.0f;
     c.exp23 = 0x4B000000u;
+    c.k0 = kMagicB + (float)k[4] * 65792.0f;
     return c;
 }
 
@@ -190,9 +192,18 @@ int process_range(fra_ctx *ctx, const int16_t *d_in, int c0, int nch, int contin
         if (ctx->flags & FRA_K1_FORCE_LANE) variant = 0;
         if (ctx->flags & FRA_K1_FORCE_SPLIT) variant = 1;
         if (ctx->flags & FRA_K1_FORCE_STAGE) variant = 2;
+        if (ctx->flags & FRA_K1_FORCE_DUO) variant = 3;
         const int8_t *bank = (ctx->mode == FRA_MODE_BANK0) ? kBank0 : ctx->bank1;
         const bool b1z = bank[1] == 0 && bank[7] == 0;          // x[n-1] coefficient zero in both sets: skip that product
-        if (variant == 2) {
+        if (variant == 3) {
+            const int grid = (nch + 31) / 32;
+            // two-instruction recurrence when both y[n-1] coefficients are small enough (fra_common.cuh)
+            const bool fast = std::abs((int)bank[4]) <= kFastMaxA1 && std::abs((int)bank[10]) <= kFastMaxA1;
+            auto kfn = fast ? (b1z ? k1_duo<true, true> : k1_duo<false, true>)
+                            : (b1z ? k1_duo<true, false> : k1_duo<false, false>);
+            FRA_TRY(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kDuoSmemBytes));
+            FRA_LAUNCH(kfn, dim3(grid), dim3(kDuoWarps * 32), (size_t)kDuoSmemBytes, st, k1);
+        } else if (variant == 2) {
             const int grid = (nch + 31) / 32;
             auto kfn = b1z ? k1_stage<true> : k1_stage<false>;
             FRA_TRY(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageSmemBytes));

@@ -42,7 +42,12 @@ struct StageCoef {
     float na0, na1;      // -A0/128 -> y[n-2], -A1/128 -> y[n-1]
     unsigned exp23;      // 0x4B000000, passed as data so that it lives in a register and
                          // PRMT's selector can be the immediate (one instruction, no re-materialised selector)
+    float k0;            // kMagicB + A1 * 65792: accumulator start for biquad_step_fast
 };
+
+// biquad_step_fast is usable when kMagicB + A1 * 65792 +- (the partial sums, < 2^17.4) stays
+// inside [2^23, 2^24)
+constexpr int kFastMaxA1 = 60;
 
 struct CascadeCoef {
     StageCoef set[2];    // set 0 (ALPHA): stages 1,3,5; set 1 (BETA): stages 2,4,6
@@ -83,6 +88,31 @@ FRA_DEV float biquad_step(float x, const StageCoef &k, StageState &s, float *y_o
     float y = wrap16_to_float(acc, k.exp23);
     s.x2 = s.x1; s.x1 = x;
     s.y2 = s.y1; s.y1 = y;
+    *y_out = y;
+    return acc;
+}
+
+// The same step with a two-instruction recurrence.  PRMT's output u = y + kBias16 (the wrapped
+// value still carrying the exponent bias) is fed to the y[n-1] product as it is:
+//   u * na1 = y * na1 + kBias16 * na1,   kBias16 * na1 = -A1 * 65792, an integer,
+// so with the accumulator started at k0 = kMagicB + A1 * 65792 the FFMA's exact sum is the
+// one biquad_step forms and, while every partial result stays inside [2^23, 2^24)
+// (|A1| <= kFastMaxA1), its single rounding gives the same integer.  The FADD that removes the
+// bias now feeds only the later uses of y (y[n-2] product, next stage, output): the loop-carried
+// chain is FFMA -> PRMT (~9.5 cycles) instead of FFMA -> PRMT -> FADD (14.2).
+template <bool B1Z = false>
+FRA_DEV float biquad_step_fast(float x, const StageCoef &k, StageState &s, float &u1, float *y_out)
+{
+    float acc = __fmaf_rd(s.x2, k.b0, k.k0);
+    if (!B1Z) acc = __fmaf_rd(s.x1, k.b1, acc);
+    acc = __fmaf_ru(s.y2, k.na0, acc);
+    acc = __fmaf_rd(x, k.b2, acc);
+    acc = __fmaf_ru(u1, k.na1, acc);
+    const float u = __uint_as_float(__byte_perm(__float_as_uint(acc), k.exp23, 0x7610));
+    const float y = u - kBias16;
+    s.x2 = s.x1; s.x1 = x;
+    s.y2 = s.y1; s.y1 = y;
+    u1 = u;
     *y_out = y;
     return acc;
 }

@@ -7,6 +7,7 @@
 //
 // Three kernels, same arithmetic (fra_common.cuh):
 //   k1_stage  one warp per stage, one lane per channel, chunks handed from warp to warp
+//   k1_duo    k1_stage with two stages per warp (two independent chains per instruction stream)
 //             through shared memory: the kernel for channel counts that cannot fill
 //             the machine with k1_lane (the 4096-channel configuration).
 //   k1_lane   one warp lane per channel, all six stages in the lane's registers.
@@ -579,6 +580,250 @@ __global__ void __launch_bounds__(kStageWarps * 32, 2) k1_stage(K1Args a)
             v.x = pack16((unsigned)(int)st.x1, (unsigned)(int)st.x2);
             v.y = pack16((unsigned)(int)st.y1, (unsigned)(int)st.y2);
             *reinterpret_cast<uint2 *>(a.state + ((size_t)c * kStages + s) * 4) = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ k1_duo
+// k1_stage with TWO stages per warp, chained in registers.  A warp that runs one biquad
+// recurrence is bound by the latency of its dependency chain (FFMA -> PRMT -> FADD, ~14-16
+// cycles per sample for 7.5 issue slots); k1_stage hides that by putting two stage warps on a
+// scheduler, and all eight warps then queue on the shared-memory pipe (12 tile accesses per
+// sample and CTA, l1tex ~2/3 busy).  Here a stage warp runs stages 2w and 2w+1 on the same
+// sample stream: stage 2w+1's recurrence trails stage 2w's by one sample, so the warp carries
+// two dependency chains that overlap, the value between them never leaves the register
+// file, and the tile traffic drops (4 boundaries instead of 6).  CTA = 5 warps: loader, 3
+// stage pairs on a scheduler each, writer; one CTA per SM for up to 148 x 32 channels.
+constexpr int kDuoPairs = kStages / 2;
+constexpr int kDuoWarps = 2 + kDuoPairs;                // loader, three stage pairs, writer
+constexpr int kDuoBoundaries = kDuoPairs + 1;           // loader -> pair 0 -> pair 1 -> pair 2 -> loader
+constexpr int kDuoTilesBytes = kDuoBoundaries * 2 * kStageTileFloats * (int)sizeof(float);    // 64 KiB
+// Global memory is touched in whole 128-byte lines only: a chunk of one channel IS one line
+// (64 int16), so eight lanes move a channel's line and one warp instruction covers four
+// channels (4 LSU tags instead of the 32 of a lane-per-channel access; every sector is moved
+// once and written whole).  Lines are staged in shared memory as [channel][8 pieces of 16 B],
+// the piece index XOR-swizzled with (channel & 7) so that the lane-per-channel side (loader
+// convert, last stage's packed output) is conflict-free too.
+constexpr int kDuoLineTileBytes = 32 * 128;              // one chunk of 32 channels as int16
+constexpr int kDuoRomBytes = kStageChunk * 4;             // the chunk's 64 window ROM entries (int32)
+constexpr int kDuoInOff = kDuoTilesBytes;                                   // raw input lines, 2 buffers
+constexpr int kDuoRomOff = kDuoInOff + 2 * kDuoLineTileBytes;               // ROM slices, 2 buffers
+constexpr int kDuoOutOff = kDuoRomOff + 2 * kDuoRomBytes;                   // packed output lines (loader-private)
+constexpr int kDuoSmemBytes = kDuoOutOff + kDuoLineTileBytes;               // 76.5 KiB
+
+FRA_DEV int duo_swz(int row, int piece) { return row * 128 + ((piece ^ (row & 7)) << 4); }
+
+// Every stage warp runs the SAME branch-free straight-line chunk body: the last pair also
+// leaves its output as a float tile, and the loader warp (which has the spare issue slots)
+// packs it to int16.  Two earlier versions are why: per-role instantiations overflowed the
+// 32 KB instruction-cache level ("no_instruction" 2.2 of 4.3 stall slots), and a run-time
+// `last` branch per group is a basic-block boundary that drains both dependency chains four
+// times per chunk (21.4 instead of 17.9 cycles per sample).
+// one stage of a pair: the exact step, or its two-instruction-recurrence form (u = y + kBias16)
+template <bool B1Z, bool FAST>
+FRA_DEV float duo_step(float x, const StageCoef &k, StageState &s, float &u)
+{
+    float y;
+    if (FAST) (void)biquad_step_fast<B1Z>(x, k, s, u, &y);
+    else (void)biquad_step<B1Z>(x, k, s, &y);
+    return y;
+}
+
+template <bool B1Z, bool FAST>
+FRA_DEV void duo_group16(const float4 (&in)[4], const StageCoef &ka, const StageCoef &kb, StageState &sa,
+                         StageState &sb, float &ua, float &ub, float4 *tout)
+{
+    float y[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        y[4 * q + 0] = duo_step<B1Z, FAST>(duo_step<B1Z, FAST>(in[q].x, ka, sa, ua), kb, sb, ub);
+        y[4 * q + 1] = duo_step<B1Z, FAST>(duo_step<B1Z, FAST>(in[q].y, ka, sa, ua), kb, sb, ub);
+        y[4 * q + 2] = duo_step<B1Z, FAST>(duo_step<B1Z, FAST>(in[q].z, ka, sa, ua), kb, sb, ub);
+        y[4 * q + 3] = duo_step<B1Z, FAST>(duo_step<B1Z, FAST>(in[q].w, ka, sa, ua), kb, sb, ub);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) tout[q * 32] = make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
+}
+
+// one chunk (64 samples) through a stage pair, straight-line like stage_chunk
+template <bool B1Z, bool FAST>
+FRA_DEV void duo_chunk(const float4 *tin, float4 *tout, const StageCoef &ka, const StageCoef &kb, StageState &sa,
+                       StageState &sb, float &ua, float &ub)
+{
+    float4 buf[2][4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) buf[0][q] = tin[q * 32];
+#pragma unroll
+    for (int g = 0; g < kStageChunk / 16; ++g) {
+        if (g + 1 < kStageChunk / 16) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) buf[(g + 1) & 1][q] = tin[((g + 1) * 4 + q) * 32];
+        }
+        duo_group16<B1Z, FAST>(buf[g & 1], ka, kb, sa, sb, ua, ub, tout + (g * 4) * 32);
+    }
+}
+
+// loader, input side: chunk t+1's lines are requested (cp.async, whole lines) before chunk t
+// is windowed and converted into the loader->pair-0 tile
+FRA_DEV void duo_loader_request(const K1Args &a, int c0, int t, unsigned char *smem_raw, int lane)
+{
+    unsigned char *dst = smem_raw + kDuoInOff + (t & 1) * kDuoLineTileBytes;
+    const int p = lane & 7;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = 4 * i + (lane >> 3);
+        const int ch = min(c0 + r, a.channels - 1);                       // clamped: rows past the end read valid memory
+        cp_async16(dst + duo_swz(r, p), a.in + (size_t)ch * a.n + (size_t)t * kStageChunk + 8 * p);
+    }
+    if (lane < 16)
+        cp_async16(smem_raw + kDuoRomOff + (t & 1) * kDuoRomBytes + 16 * lane,
+                   a.rom32 + (((t * kStageChunk) & (kWindowLen - 1)) + 4 * lane));
+}
+
+// (all shared-memory loads of a batch are issued before the first store: the compiler cannot
+// move a load above a store to memory it cannot tell apart, and a load -> convert -> store
+// sequence per piece costs one full shared-memory latency each)
+template <bool QUIRK>
+FRA_DEV void duo_convert_chunk(const unsigned char *lines, const int4 *rom, float4 *tile, int lane)
+{
+    uint4 x[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) x[q] = *reinterpret_cast<const uint4 *>(lines + duo_swz(lane, q));
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        int4 r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = rom[8 * h + j];            // same address in every lane: broadcast
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int q = 4 * h + j;
+            float4 fa, fb;
+            stage_convert8<QUIRK>(x[q], r[2 * j], r[2 * j + 1], fa, fb);
+            tile[(2 * q) * 32] = fa;
+            tile[(2 * q + 1) * 32] = fb;
+        }
+    }
+}
+
+// writer warp: the last pair's float tile of chunk `chunk` -> int16 lines (swizzled
+// staging, lane per channel) -> global memory, whole lines (eight lanes per channel)
+FRA_DEV void duo_store_chunk(const K1Args &a, int c0, int chunk, unsigned char *smem_raw, int lane)
+{
+    const float4 *tile = stage_tile(reinterpret_cast<float *>(smem_raw), kDuoPairs, chunk & 1) + lane;
+    unsigned char *lines = smem_raw + kDuoOutOff;
+    auto pk = [](float u, float v) {           // u + 1.5 * 2^23 holds u mod 2^16 in its low mantissa bits
+        return pack16(__float_as_uint(u + kMagic), __float_as_uint(v + kMagic));
+    };
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        float4 f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = tile[(8 * h + j) * 32];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint4 o;
+            o.x = pk(f[2 * j].x, f[2 * j].y);
+            o.y = pk(f[2 * j].z, f[2 * j].w);
+            o.z = pk(f[2 * j + 1].x, f[2 * j + 1].y);
+            o.w = pk(f[2 * j + 1].z, f[2 * j + 1].w);
+            *reinterpret_cast<uint4 *>(lines + duo_swz(lane, 4 * h + j)) = o;
+        }
+    }
+    __syncwarp();
+    const int p = lane & 7;
+    uint4 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const uint4 *>(lines + duo_swz(4 * i + (lane >> 3), p));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int ch = c0 + 4 * i + (lane >> 3);
+        if (ch < a.channels) stg128(a.out + (size_t)ch * a.n + (size_t)chunk * kStageChunk + 8 * p, v[i]);
+    }
+    __syncwarp();                                              // the staging lines are reused next step
+}
+
+FRA_DEV void duo_loader_step(const K1Args &a, int c0, int t, int n_chunks, unsigned char *smem_raw, int lane)
+{
+    if (t >= n_chunks) return;
+    if (t + 1 < n_chunks) duo_loader_request(a, c0, t + 1, smem_raw, lane);
+    cp_async_commit();
+    cp_async_wait<1>();                                        // everything but the group just committed: chunk t is here
+    __syncwarp();                                              // each line was copied by eight different lanes
+    const unsigned char *lines = smem_raw + kDuoInOff + (t & 1) * kDuoLineTileBytes;
+    const int4 *rom = reinterpret_cast<const int4 *>(smem_raw + kDuoRomOff + (t & 1) * kDuoRomBytes);
+    float4 *tile = stage_tile(reinterpret_cast<float *>(smem_raw), 0, t & 1) + lane;
+    const int w0 = (t * kStageChunk) & (kWindowLen - 1);
+    // ROM entries equal to -32768 live in [0, 15), [8178, 8206) and at 16383
+    const bool quirk = (w0 < 64) || (w0 >= 8128 && w0 < 8256) || (w0 >= kWindowLen - 64);
+    if (quirk) duo_convert_chunk<true>(lines, rom, tile, lane);
+    else duo_convert_chunk<false>(lines, rom, tile, lane);
+}
+
+FRA_DEV StageState duo_load_state(const K1Args &a, int cc, int s)
+{
+    StageState st = {0.0f, 0.0f, 0.0f, 0.0f};
+    if (a.continuous) {
+        const uint2 v = __ldg(reinterpret_cast<const uint2 *>(a.state + ((size_t)cc * kStages + s) * 4));
+        st.x1 = small_int_to_float(lo16(v.x));
+        st.x2 = small_int_to_float(hi16(v.x));
+        st.y1 = small_int_to_float(lo16(v.y));
+        st.y2 = small_int_to_float(hi16(v.y));
+    }
+    return st;
+}
+
+FRA_DEV void duo_store_state(const K1Args &a, int c, int s, const StageState &st)
+{
+    uint2 v;
+    v.x = pack16((unsigned)(int)st.x1, (unsigned)(int)st.x2);
+    v.y = pack16((unsigned)(int)st.y1, (unsigned)(int)st.y2);
+    *reinterpret_cast<uint2 *>(a.state + ((size_t)c * kStages + s) * 4) = v;
+}
+
+template <bool B1Z, bool FAST>
+__global__ void __launch_bounds__(kDuoWarps * 32, 1) k1_duo(K1Args a)
+{
+    FRA_DYN_SMEM(smem_raw);
+    float *smem = reinterpret_cast<float *>(smem_raw);
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int c0 = blockIdx.x * 32;
+    const int c = c0 + lane;
+    const bool live = c < a.channels;
+    const int cc = live ? c : (a.channels - 1);
+    const int n_chunks = a.n / kStageChunk;
+    const int n_steps = n_chunks + kDuoPairs + 1;                 // + fill of the three pairs + the writer's last chunk
+
+    if (warp == 0) {
+        duo_loader_request(a, c0, 0, smem_raw, lane);
+        cp_async_commit();
+        for (int t = 0; t < n_steps; ++t) {
+            duo_loader_step(a, c0, t, n_chunks, smem_raw, lane);
+            __syncthreads();
+        }
+    } else if (warp == kDuoWarps - 1) {
+        // shares the loader's scheduler: both are short, latency-bound instruction streams
+        for (int t = 0; t < n_steps; ++t) {
+            const int done = t - (kDuoPairs + 1);                // the chunk the last pair finished in the step before
+            if (done >= 0) duo_store_chunk(a, c0, done, smem_raw, lane);
+            __syncthreads();
+        }
+    } else {
+        const int p = warp - 1;                                  // stage pair: stages 2p and 2p+1
+        const StageCoef ka = a.coef.set[0], kb = a.coef.set[1];
+        StageState sa = duo_load_state(a, cc, 2 * p), sb = duo_load_state(a, cc, 2 * p + 1);
+        float ua = sa.y1 + kBias16, ub = sb.y1 + kBias16;
+        for (int t = 0; t < n_steps; ++t) {
+            const int chunk = t - 1 - p;
+            if (chunk >= 0 && chunk < n_chunks) {
+                duo_chunk<B1Z, FAST>(stage_tile(smem, p, chunk & 1) + lane, stage_tile(smem, p + 1, chunk & 1) + lane,
+                                     ka, kb, sa, sb, ua, ub);
+            }
+            __syncthreads();
+        }
+        if (live) {
+            duo_store_state(a, c, 2 * p, sa);
+            duo_store_state(a, c, 2 * p + 1, sb);
         }
     }
 }

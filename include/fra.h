@@ -62,6 +62,7 @@ typedef enum fra_status {
 #define FRA_ROUND_NEAREST   0x1u     /* int16 bins rounded to nearest-even instead of truncated (floor) */
 #define FRA_K1_FORCE_LANE   0x2u     /* always use the lane-per-channel window+IIR kernel */
 #define FRA_K1_FORCE_STAGE  0x10u    /* always use the warp-per-stage pipeline window+IIR kernel */
+#define FRA_K1_FORCE_DUO    0x20u    /* always use the two-stages-per-warp pipeline window+IIR kernel */
 #define FRA_K1_FORCE_SPLIT  0x4u     /* always use the stage-per-lane (systolic) window+IIR kernel */
 #define FRA_K1_SPECULATE    0x8u     /* systolic kernel: try the no-overflow recurrence (FFMA->FADD) first and roll a block
                                         back when a sum left the int16 range; same results, measured no faster on B200 */

@@ -57,6 +57,22 @@ int main()
             unsigned w2 = pack16_acc(kMagicB + (float)a, kMagicB + (float)b);
             if (lo16(w2) != a || hi16(w2) != b) ++bad;
         }
+    // 6. biquad_step_fast's biased y[n-1] product: for every |A1| <= kFastMaxA1 and every int16 y,
+    //    fma.ru(y + kBias16, -A1/128, k0 + s4) == kMagicB + s4 - floor(y*A1/128), with the partial
+    //    sum s4 of the four earlier terms at its extremes (|T| <= 2^15 each) and at zero
+    for (int a1 = -kFastMaxA1; a1 <= kFastMaxA1; ++a1) {
+        const float na1 = -(float)a1 / 128.0f, k0 = kMagicB + (float)a1 * 65792.0f;
+        for (int y = -32768; y <= 32767; ++y) {
+            const int f = floordiv128(y * a1);
+            for (int s4 : {-4 * 32768, -1, 0, 1, 4 * 32768}) {
+                const float got = __fmaf_ru((float)y + kBias16, na1, k0 + (float)s4);
+                if (got != kMagicB + (float)(s4 - f)) {
+                    if (bad < 20) std::printf("fast-step mismatch a1=%d y=%d s4=%d got=%f\n", a1, y, s4, got);
+                    ++bad;
+                }
+            }
+        }
+    }
     std::printf("bad=%ld\n", bad);
     return bad ? 1 : 0;
 }

@@ -24,7 +24,7 @@ def adversarial(rng, c, n):
 
 
 @pytest.mark.parametrize("flags,name", [(_abi.FRA_K1_FORCE_LANE, "lane"), (_abi.FRA_K1_FORCE_SPLIT, "split"),
-                                        (_abi.FRA_K1_FORCE_STAGE, "stage")])
+                                        (_abi.FRA_K1_FORCE_STAGE, "stage"), (_abi.FRA_K1_FORCE_DUO, "duo")])
 @pytest.mark.parametrize("channels", [1, 6, 37])
 def test_k1_bit_exact_with_state_and_reload(flags, name, channels, rom):
     rng = np.random.default_rng(channels)
@@ -54,11 +54,15 @@ def test_k1_bit_exact_with_state_and_reload(flags, name, channels, rom):
 def test_k1_random_coefficients_and_user_state(rom):
     rng = np.random.default_rng(7)
     n, c = 1024, 7
-    for trial in range(3):
+    for trial in range(5):
         coef = rng.integers(-128, 128, 12).astype(np.int8)
         if trial == 0:
             coef[:] = [-128, 127, -128, -128, 127, 0, 127, -128, 127, 127, -128, 0]
-        for flags in (_abi.FRA_K1_FORCE_LANE, _abi.FRA_K1_FORCE_SPLIT, _abi.FRA_K1_FORCE_STAGE,
+        if trial == 3:      # |A1| at the limit of the two-instruction recurrence (k1_duo FAST), the rest extreme
+            coef[:] = [-128, 127, -128, -128, 60, 0, 127, -128, 127, 127, -60, 0]
+        if trial == 4:
+            coef[4], coef[10] = rng.integers(-60, 61, 2)
+        for flags in (_abi.FRA_K1_FORCE_LANE, _abi.FRA_K1_FORCE_SPLIT, _abi.FRA_K1_FORCE_STAGE, _abi.FRA_K1_FORCE_DUO,
                       _abi.FRA_K1_FORCE_SPLIT | _abi.FRA_K1_SPECULATE):      # speculation must roll back correctly
             f = EmulFra(c, n, flags)
             try:

@@ -43,11 +43,11 @@ def rel_l2(got, ref):
     return float(np.linalg.norm(got - ref) / np.linalg.norm(ref))
 
 
-@pytest.mark.parametrize("variant", ["lane", "split", "stage"])
+@pytest.mark.parametrize("variant", ["lane", "split", "stage", "duo"])
 @pytest.mark.parametrize("channels", [1, 5, 33, 257])
 def test_k1_bit_exact_state_reload(fra, rom, variant, channels):
     flags = {"lane": fra._abi.FRA_K1_FORCE_LANE, "split": fra._abi.FRA_K1_FORCE_SPLIT,
-             "stage": fra._abi.FRA_K1_FORCE_STAGE}[variant]
+             "stage": fra._abi.FRA_K1_FORCE_STAGE, "duo": fra._abi.FRA_K1_FORCE_DUO}[variant]
     rng = np.random.default_rng(channels)
     n = 16384
     with fra.FraContext(channels, n, flags=flags) as ctx:
@@ -79,7 +79,14 @@ def test_k1_random_int8_coefficients_fuzz(fra, rom, seed):
     coef = rng.integers(-128, 128, 12).astype(np.int8)
     if seed == 1:
         coef[:] = [-128, 127, -128, -128, 127, 0, 127, -128, 127, 127, -128, 0]
+    if seed == 5:           # |A1| at the limit of k1_duo's two-instruction recurrence, the rest extreme
+        coef[:] = [-128, 127, -128, -128, 60, 0, 127, -128, 127, 127, -60, 0]
+    if seed == 6:
+        coef[:] = [127, -128, 127, 127, -60, 0, -128, 127, -128, -128, 60, 0]
+    if seed >= 7:
+        coef[4], coef[10] = rng.integers(-60, 61, 2)
     for flags in (fra._abi.FRA_K1_FORCE_LANE, fra._abi.FRA_K1_FORCE_SPLIT, fra._abi.FRA_K1_FORCE_STAGE,
+                  fra._abi.FRA_K1_FORCE_DUO,
                   fra._abi.FRA_K1_FORCE_SPLIT | fra._abi.FRA_K1_SPECULATE):
         with fra.FraContext(c, n, flags=flags) as ctx:
             ctx.load_bank1(coef)

@@ -19,7 +19,7 @@ ap.add_argument("--k1", default="auto")
 ap.add_argument("--time", action="store_true")
 a = ap.parse_args()
 flags = {"auto": 0, "lane": _abi.FRA_K1_FORCE_LANE, "split": _abi.FRA_K1_FORCE_SPLIT,
-         "spec": _abi.FRA_K1_SPECULATE | _abi.FRA_K1_FORCE_SPLIT, "stage": _abi.FRA_K1_FORCE_STAGE}[a.k1]
+         "spec": _abi.FRA_K1_SPECULATE | _abi.FRA_K1_FORCE_SPLIT, "stage": _abi.FRA_K1_FORCE_STAGE, "duo": _abi.FRA_K1_FORCE_DUO}[a.k1]
 ctx = FraContext(a.channels, a.n, flags=flags)
 ctx.command(int(a.mode, 16))
 xs = [synth.tone_noise(a.channels, a.n, "cuda", frame=i) for i in range(2)]
