@@ -30,7 +30,7 @@ const int16_t kHannRom[kWindowLen] = {
 const int8_t kBank0[12] = {-14, 0, 14, 107, 21, 127, -15, 0, 15, 107, -21, 127};
 
 constexpr int kStreamMaxDeadband = 32;            // LSB; larger boundary differences mean the scan is invalid
-constexpr int kLaneMinChannels = 22000;          // measured crossover: below it k1_stage (0.045 us/channel) beats k1_lane (flat 1.0 ms)
+constexpr int kLaneMinChannels = 28672;          // measured crossover: below it k1_duo (0.034 us/channel at two CTAs per SM) beats k1_lane (flat 1.0 ms)
 
 }  // namespace
 
@@ -186,9 +186,9 @@ int process_range(fra_ctx *ctx, const int16_t *d_in, int c0, int nch, int contin
         k1.continuous = continuous;
         k1.speculate = (ctx->flags & FRA_K1_SPECULATE) ? 1 : 0;
         if (ctx->profiling) FRA_TRY(ctx, cudaEventRecord(ctx->ev[0], st));
-        // k1_lane needs ~19k channels to fill 592 schedulers; below that the stage-per-warp
-        // pipeline; the stage-per-lane systolic kernel only on request (and for one stream)
-        int variant = (nch < kLaneMinChannels) ? 2 : 0;          // 0 lane, 1 split, 2 stage
+        // k1_lane needs ~19k channels to fill 592 schedulers; below that the stage-pair-per-warp
+        // pipeline k1_duo; k1_stage and the stage-per-lane systolic k1_split only on request
+        int variant = (nch < kLaneMinChannels) ? 3 : 0;          // 0 lane, 1 split, 2 stage, 3 duo
         if (ctx->flags & FRA_K1_FORCE_LANE) variant = 0;
         if (ctx->flags & FRA_K1_FORCE_SPLIT) variant = 1;
         if (ctx->flags & FRA_K1_FORCE_STAGE) variant = 2;
@@ -201,8 +201,9 @@ int process_range(fra_ctx *ctx, const int16_t *d_in, int c0, int nch, int contin
             const bool fast = std::abs((int)bank[4]) <= kFastMaxA1 && std::abs((int)bank[10]) <= kFastMaxA1;
             auto kfn = fast ? (b1z ? k1_duo<true, true> : k1_duo<false, true>)
                             : (b1z ? k1_duo<true, false> : k1_duo<false, false>);
-            FRA_TRY(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kDuoSmemBytes));
-            FRA_LAUNCH(kfn, dim3(grid), dim3(kDuoWarps * 32), (size_t)kDuoSmemBytes, st, k1);
+            static_assert(kDuoSmemRequest >= kDuoSmemBytes, "k1_duo shared memory");
+            FRA_TRY(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kDuoSmemRequest));
+            FRA_LAUNCH(kfn, dim3(grid), dim3(kDuoWarps * 32), (size_t)kDuoSmemRequest, st, k1);
         } else if (variant == 2) {
             const int grid = (nch + 31) / 32;
             auto kfn = b1z ? k1_stage<true> : k1_stage<false>;

@@ -593,7 +593,8 @@ __global__ void __launch_bounds__(kStageWarps * 32, 2) k1_stage(K1Args a)
 // sample stream: stage 2w+1's recurrence trails stage 2w's by one sample, so the warp carries
 // two dependency chains that overlap, the value between them never leaves the register
 // file, and the tile traffic drops (4 boundaries instead of 6).  CTA = 5 warps: loader, 3
-// stage pairs on a scheduler each, writer; one CTA per SM for up to 148 x 32 channels.
+// stage pairs on a scheduler each, writer; one CTA per SM for up to 148 x 32 channels, two
+// per SM beyond that.
 constexpr int kDuoPairs = kStages / 2;
 constexpr int kDuoWarps = 2 + kDuoPairs;                // loader, three stage pairs, writer
 constexpr int kDuoBoundaries = kDuoPairs + 1;           // loader -> pair 0 -> pair 1 -> pair 2 -> loader
@@ -608,8 +609,10 @@ constexpr int kDuoLineTileBytes = 32 * 128;              // one chunk of 32 chan
 constexpr int kDuoRomBytes = kStageChunk * 4;             // the chunk's 64 window ROM entries (int32)
 constexpr int kDuoInOff = kDuoTilesBytes;                                   // raw input lines, 2 buffers
 constexpr int kDuoRomOff = kDuoInOff + 2 * kDuoLineTileBytes;               // ROM slices, 2 buffers
-constexpr int kDuoOutOff = kDuoRomOff + 2 * kDuoRomBytes;                   // packed output lines (loader-private)
-constexpr int kDuoSmemBytes = kDuoOutOff + kDuoLineTileBytes;               // 76.5 KiB
+constexpr int kDuoSmemBytes = kDuoRomOff + 2 * kDuoRomBytes;                // 72.5 KiB
+// requested size: padded so that at most TWO CTAs share an SM - a third adds no throughput (the
+// three stage-pair schedulers are issue-bound with two) and makes the tail wave longer
+constexpr int kDuoSmemRequest = 77 * 1024;
 
 FRA_DEV int duo_swz(int row, int piece) { return row * 128 + ((piece ^ (row & 7)) << 4); }
 
@@ -705,15 +708,19 @@ FRA_DEV void duo_convert_chunk(const unsigned char *lines, const int4 *rom, floa
     }
 }
 
-// writer warp: the last pair's float tile of chunk `chunk` -> int16 lines (swizzled
-// staging, lane per channel) -> global memory, whole lines (eight lanes per channel)
+// writer warp: the last pair's float tile of chunk `chunk` -> int16 lines (swizzled, lane per
+// channel) -> global memory, whole lines (eight lanes per channel).  The lines are staged in
+// the first half of the float tile itself, once every lane has read its part of it: the last
+// pair will not write this parity again before the next barrier.
 FRA_DEV void duo_store_chunk(const K1Args &a, int c0, int chunk, unsigned char *smem_raw, int lane)
 {
-    const float4 *tile = stage_tile(reinterpret_cast<float *>(smem_raw), kDuoPairs, chunk & 1) + lane;
-    unsigned char *lines = smem_raw + kDuoOutOff;
+    float4 *tile_base = stage_tile(reinterpret_cast<float *>(smem_raw), kDuoPairs, chunk & 1);
+    const float4 *tile = tile_base + lane;
+    unsigned char *lines = reinterpret_cast<unsigned char *>(tile_base);
     auto pk = [](float u, float v) {           // u + 1.5 * 2^23 holds u mod 2^16 in its low mantissa bits
         return pack16(__float_as_uint(u + kMagic), __float_as_uint(v + kMagic));
     };
+    uint4 o[8];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         float4 f[8];
@@ -721,14 +728,15 @@ FRA_DEV void duo_store_chunk(const K1Args &a, int c0, int chunk, unsigned char *
         for (int j = 0; j < 8; ++j) f[j] = tile[(8 * h + j) * 32];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            uint4 o;
-            o.x = pk(f[2 * j].x, f[2 * j].y);
-            o.y = pk(f[2 * j].z, f[2 * j].w);
-            o.z = pk(f[2 * j + 1].x, f[2 * j + 1].y);
-            o.w = pk(f[2 * j + 1].z, f[2 * j + 1].w);
-            *reinterpret_cast<uint4 *>(lines + duo_swz(lane, 4 * h + j)) = o;
+            o[4 * h + j].x = pk(f[2 * j].x, f[2 * j].y);
+            o[4 * h + j].y = pk(f[2 * j].z, f[2 * j].w);
+            o[4 * h + j].z = pk(f[2 * j + 1].x, f[2 * j + 1].y);
+            o[4 * h + j].w = pk(f[2 * j + 1].z, f[2 * j + 1].w);
         }
     }
+    __syncwarp();                                              // every lane has read the tile
+#pragma unroll
+    for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4 *>(lines + duo_swz(lane, q)) = o[q];
     __syncwarp();
     const int p = lane & 7;
     uint4 v[8];
@@ -739,7 +747,6 @@ FRA_DEV void duo_store_chunk(const K1Args &a, int c0, int chunk, unsigned char *
         const int ch = c0 + 4 * i + (lane >> 3);
         if (ch < a.channels) stg128(a.out + (size_t)ch * a.n + (size_t)chunk * kStageChunk + 8 * p, v[i]);
     }
-    __syncwarp();                                              // the staging lines are reused next step
 }
 
 FRA_DEV void duo_loader_step(const K1Args &a, int c0, int t, int n_chunks, unsigned char *smem_raw, int lane)
@@ -781,7 +788,7 @@ FRA_DEV void duo_store_state(const K1Args &a, int c, int s, const StageState &st
 }
 
 template <bool B1Z, bool FAST>
-__global__ void __launch_bounds__(kDuoWarps * 32, 1) k1_duo(K1Args a)
+__global__ void __launch_bounds__(kDuoWarps * 32, 2) k1_duo(K1Args a)
 {
     FRA_DYN_SMEM(smem_raw);
     float *smem = reinterpret_cast<float *>(smem_raw);
