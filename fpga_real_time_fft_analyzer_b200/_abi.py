@@ -33,6 +33,7 @@ FRA_K1_FORCE_SPLIT = 0x4
 FRA_K1_SPECULATE = 0x8
 FRA_K1_FORCE_STAGE = 0x10
 FRA_K1_FORCE_DUO = 0x20
+FRA_PIPELINE = 0x40
 
 
 class FraOutputs(C.Structure):
@@ -70,6 +71,7 @@ SIGNATURES = {
     "fra_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "fra_profile_last": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "fra_sync": (C.c_int, [C.c_void_p]),
+    "fra_join": (C.c_int, [C.c_void_p, C.c_void_p]),
     "fra_last_kernel_count": (C.c_int, [C.c_void_p]),
     "fra_last_cuda_error": (C.c_char_p, [C.c_void_p]),
     "fra_strerror": (C.c_char_p, [C.c_int]),

@@ -221,7 +221,15 @@ class FraContext:
         return a.value, b.value
 
     def sync(self):
+        """Host waits for everything the context has enqueued."""
         self._check(self._L.fra_sync(self._h), "fra_sync")
+
+    def join(self):
+        """FRA_PIPELINE contexts: torch's current stream waits (on the device) for all work
+        enqueued by earlier process() calls; outputs may be read on that stream afterwards."""
+        import torch
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self._check(self._L.fra_join(self._h, C.c_void_p(stream)), "fra_join")
 
     @property
     def last_kernel_count(self) -> int:

@@ -68,6 +68,12 @@ struct fra_ctx {
     int *d_counts = nullptr;
     int k1b_capacity = 0;
 
+    // FRA_PIPELINE: window+IIR of call i+1 beside the FFT of call i
+    cudaStream_t pipe_k1 = nullptr, pipe_k2 = nullptr;
+    cudaEvent_t pipe_in = nullptr, pipe_k1_done[2] = {nullptr, nullptr}, pipe_k2_done[2] = {nullptr, nullptr};
+    unsigned long long pipe_calls = 0;
+    size_t scratch_elems = 0;         // int16 elements allocated at d_scratch
+
     bool profiling = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // K1 begin/end, K2 begin/end
     bool ev_k1 = false, ev_k2 = false;
@@ -165,16 +171,21 @@ int launch_k2(fra_ctx *ctx, const K2Args &args, bool win, int qmode, cudaStream_
 
 // One step over channels [c0, c0 + nch): pointers in `o` and d_in are already
 // offset to channel c0.
+// st: stream of the window+IIR kernel; st2 / k1_done: when given, the FFT kernel runs on st2
+// after k1_done (recorded on st behind the window+IIR kernel); scratch: filter output buffer
+// for the whole context when the caller does not ask for it
 int process_range(fra_ctx *ctx, const int16_t *d_in, int c0, int nch, int continuous, int log2_scale,
-                  const fra_outputs &o, cudaStream_t st)
+                  const fra_outputs &o, cudaStream_t st, cudaStream_t st2 = nullptr, cudaEvent_t k1_done = nullptr,
+                  int16_t *scratch = nullptr)
 {
+    if (!scratch) scratch = ctx->d_scratch;
     const int n = ctx->n;
     const bool iir = (ctx->mode == FRA_MODE_BANK0 || ctx->mode == FRA_MODE_BANK1);
     const bool want_fft = o.d_frames || o.d_iq || o.d_mag || o.d_phase;
     const int16_t *fft_in = d_in;
 
     if (iir) {
-        int16_t *filt = o.d_filtered ? o.d_filtered : (ctx->d_scratch + (size_t)c0 * n);
+        int16_t *filt = o.d_filtered ? o.d_filtered : (scratch + (size_t)c0 * n);
         K1Args k1;
         k1.in = d_in;
         k1.out = filt;
@@ -237,6 +248,11 @@ int process_range(fra_ctx *ctx, const int16_t *d_in, int c0, int nch, int contin
         ctx->last_kernels++;
     }
 
+    if (k1_done) {
+        FRA_TRY(ctx, cudaEventRecord(k1_done, st));
+        FRA_TRY(ctx, cudaStreamWaitEvent(st2, k1_done, 0));
+        st = st2;
+    }
     if (want_fft) {
         K2Args k2;
         k2.in = reinterpret_cast<const uint32_t *>(fft_in);
@@ -262,6 +278,30 @@ int process_range(fra_ctx *ctx, const int16_t *d_in, int c0, int nch, int contin
         }
     }
     return FRA_OK;
+}
+
+int pipe_init(fra_ctx *ctx)
+{
+    if (ctx->pipe_k1) return FRA_OK;
+    int lo = 0, hi = 0;                                        // hi is the numerically smaller value
+    FRA_TRY(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    FRA_TRY(ctx, cudaStreamCreateWithPriority(&ctx->pipe_k1, cudaStreamNonBlocking, hi));
+    FRA_TRY(ctx, cudaStreamCreateWithPriority(&ctx->pipe_k2, cudaStreamNonBlocking, lo));
+    FRA_TRY(ctx, cudaEventCreateWithFlags(&ctx->pipe_in, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) {
+        FRA_TRY(ctx, cudaEventCreateWithFlags(&ctx->pipe_k1_done[i], cudaEventDisableTiming));
+        FRA_TRY(ctx, cudaEventCreateWithFlags(&ctx->pipe_k2_done[i], cudaEventDisableTiming));
+    }
+    return FRA_OK;
+}
+
+// host waits for the two pipeline streams (before anything that touches state or scratch
+// from another stream)
+cudaError_t pipe_host_join(fra_ctx *ctx)
+{
+    cudaError_t e = ctx->pipe_k1 ? cudaStreamSynchronize(ctx->pipe_k1) : cudaSuccess;
+    if (e == cudaSuccess && ctx->pipe_k2) e = cudaStreamSynchronize(ctx->pipe_k2);
+    return e;
 }
 
 fra_outputs offset_outputs(const fra_outputs &o, size_t c0, int n)
@@ -372,6 +412,10 @@ int fra_destroy(fra_ctx *ctx)
     if (!ctx) return FRA_ERR_INVALID;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (cudaStream_t ps : {ctx->pipe_k1, ctx->pipe_k2})
+        if (ps) { cudaStreamSynchronize(ps); cudaStreamDestroy(ps); }
+    for (cudaEvent_t pe : {ctx->pipe_in, ctx->pipe_k1_done[0], ctx->pipe_k1_done[1], ctx->pipe_k2_done[0], ctx->pipe_k2_done[1]})
+        if (pe) cudaEventDestroy(pe);
     void *bufs[] = {ctx->d_rom32, ctx->d_state, ctx->d_scratch, ctx->d_tw1, ctx->d_tw2, ctx->d_twn, ctx->d_in,
                     ctx->d_frames, ctx->d_filtered_out, ctx->d_iq, ctx->d_mag, ctx->d_phase, ctx->d_entry,
                     ctx->d_exit, ctx->d_counts, ctx->d_ends, ctx->d_aggr, ctx->d_mats};
@@ -487,17 +531,57 @@ int fra_process(fra_ctx *ctx, const int16_t *d_in, int continuous, int log2_scal
     FRA_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;      // NULL = the legacy default stream
     const bool iir = (ctx->mode == FRA_MODE_BANK0 || ctx->mode == FRA_MODE_BANK1);
-    if (iir && !out->d_filtered && !ctx->d_scratch)
-        if (cudaMalloc((void **)&ctx->d_scratch, (size_t)ctx->channels * ctx->n * sizeof(int16_t)) != cudaSuccess)
-            return FRA_ERR_NOMEM;
+    const bool pipe = (ctx->flags & FRA_PIPELINE) != 0;
+    const size_t frame_elems = (size_t)ctx->channels * ctx->n;
+    const size_t want_elems = frame_elems * (pipe ? 2 : 1);
+    if (iir && !out->d_filtered && ctx->scratch_elems < want_elems) {
+        if (pipe) FRA_TRY(ctx, pipe_host_join(ctx));
+        if (ctx->d_scratch) FRA_TRY(ctx, cudaFree(ctx->d_scratch));
+        ctx->d_scratch = nullptr;
+        ctx->scratch_elems = 0;
+        if (cudaMalloc((void **)&ctx->d_scratch, want_elems * sizeof(int16_t)) != cudaSuccess) return FRA_ERR_NOMEM;
+        ctx->scratch_elems = want_elems;
+    }
     ctx->last_kernels = 0;
     ctx->ev_k1 = ctx->ev_k2 = false;
-    return process_range(ctx, d_in, 0, ctx->channels, continuous, log2_scale, *out, st);
+    if (!pipe) return process_range(ctx, d_in, 0, ctx->channels, continuous, log2_scale, *out, st);
+
+    // ---- FRA_PIPELINE: K1(i) on pipe_k1 (high priority: its few long-lived CTAs are placed
+    // first), K2(i) on pipe_k2 behind it, so K2(i) and K1(i+1) share the SMs.  Two filter
+    // scratch buffers alternate; K1(i) waits for K2(i-2), the last reader of its buffer.
+    int rc = pipe_init(ctx);
+    if (rc != FRA_OK) return rc;
+    const int buf = (int)(ctx->pipe_calls & 1);
+    FRA_TRY(ctx, cudaEventRecord(ctx->pipe_in, st));
+    FRA_TRY(ctx, cudaStreamWaitEvent(ctx->pipe_k1, ctx->pipe_in, 0));
+    if (ctx->pipe_calls >= 2) FRA_TRY(ctx, cudaStreamWaitEvent(ctx->pipe_k1, ctx->pipe_k2_done[buf], 0));
+    // a caller-owned filter output is rewritten every call: the previous FFT must have read it
+    if (out->d_filtered && ctx->pipe_calls >= 1)
+        FRA_TRY(ctx, cudaStreamWaitEvent(ctx->pipe_k1, ctx->pipe_k2_done[buf ^ 1], 0));
+    rc = process_range(ctx, d_in, 0, ctx->channels, continuous, log2_scale, *out, ctx->pipe_k1, ctx->pipe_k2,
+                       ctx->pipe_k1_done[buf], ctx->d_scratch ? ctx->d_scratch + (size_t)buf * frame_elems : nullptr);
+    if (rc != FRA_OK) return rc;
+    FRA_TRY(ctx, cudaEventRecord(ctx->pipe_k2_done[buf], ctx->pipe_k2));
+    ctx->pipe_calls++;
+    return FRA_OK;
+}
+
+int fra_join(fra_ctx *ctx, void *cuda_stream)
+{
+    if (!ctx) return FRA_ERR_INVALID;
+    if (!(ctx->flags & FRA_PIPELINE) || ctx->pipe_calls == 0) return FRA_OK;
+    FRA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    // pipe_k2 is in order, so its newest event covers every earlier call; the window+IIR kernel of
+    // the last call finished before that call's FFT started
+    FRA_TRY(ctx, cudaStreamWaitEvent(st, ctx->pipe_k2_done[(ctx->pipe_calls - 1) & 1], 0));
+    return FRA_OK;
 }
 
 int fra_process_host(fra_ctx *ctx, const int16_t *h_in, int continuous, int log2_scale, const fra_outputs *h_out)
 {
     if (!ctx || !h_in || !h_out) return FRA_ERR_INVALID;
+    FRA_TRY(ctx, pipe_host_join(ctx));
     if (log2_scale == FRA_SCALE_DEFAULT) log2_scale = -ctx->log2n;
     if (log2_scale < -40 || log2_scale > 16) return FRA_ERR_INVALID;
     FRA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -510,7 +594,10 @@ int fra_process_host(fra_ctx *ctx, const int16_t *h_in, int continuous, int log2
     if (h_out->d_mag && !need((void **)&ctx->d_mag, C * n * 4)) return FRA_ERR_NOMEM;
     if (h_out->d_phase && !need((void **)&ctx->d_phase, C * n * 4)) return FRA_ERR_NOMEM;
     const bool iir = (ctx->mode == FRA_MODE_BANK0 || ctx->mode == FRA_MODE_BANK1);
-    if (iir && !h_out->d_filtered && !need((void **)&ctx->d_scratch, C * n * 2)) return FRA_ERR_NOMEM;
+    if (iir && !h_out->d_filtered && !ctx->d_scratch) {
+        if (cudaMalloc((void **)&ctx->d_scratch, C * n * 2) != cudaSuccess) return FRA_ERR_NOMEM;
+        ctx->scratch_elems = C * n;
+    }
 
     fra_outputs dev;
     dev.d_filtered = h_out->d_filtered ? ctx->d_filtered_out : nullptr;
@@ -557,6 +644,7 @@ int fra_get_state(fra_ctx *ctx, int16_t *d_state, void *cuda_stream)
 {
     if (!ctx || !d_state) return FRA_ERR_INVALID;
     FRA_TRY(ctx, cudaSetDevice(ctx->device));
+    FRA_TRY(ctx, pipe_host_join(ctx));                 // FRA_PIPELINE: the state belongs to pipe_k1 until it drains
     cudaStream_t st = (cudaStream_t)cuda_stream;      // NULL = the legacy default stream
     FRA_TRY(ctx, cudaMemcpyAsync(d_state, ctx->d_state, (size_t)ctx->channels * 24 * sizeof(int16_t),
                                  cudaMemcpyDeviceToDevice, st));
@@ -567,6 +655,7 @@ int fra_set_state(fra_ctx *ctx, const int16_t *d_state, void *cuda_stream)
 {
     if (!ctx || !d_state) return FRA_ERR_INVALID;
     FRA_TRY(ctx, cudaSetDevice(ctx->device));
+    FRA_TRY(ctx, pipe_host_join(ctx));                 // FRA_PIPELINE: the state belongs to pipe_k1 until it drains
     cudaStream_t st = (cudaStream_t)cuda_stream;      // NULL = the legacy default stream
     FRA_TRY(ctx, cudaMemcpyAsync(ctx->d_state, d_state, (size_t)ctx->channels * 24 * sizeof(int16_t),
                                  cudaMemcpyDeviceToDevice, st));
@@ -578,6 +667,7 @@ int fra_iir_stream(fra_ctx *ctx, const int16_t *d_in, int16_t *d_out, size_t n, 
 {
     if (!ctx || !d_in || !d_out || n == 0 || (n % 8) != 0) return FRA_ERR_INVALID;
     FRA_TRY(ctx, cudaSetDevice(ctx->device));
+    FRA_TRY(ctx, pipe_host_join(ctx));
     cudaStream_t st = ctx->stream;
     const bool iir = (ctx->mode == FRA_MODE_BANK0 || ctx->mode == FRA_MODE_BANK1);
     const int8_t *bank = (ctx->mode == FRA_MODE_BANK1) ? ctx->bank1 : kBank0;
@@ -824,6 +914,7 @@ int fra_sync(fra_ctx *ctx)
     if (!ctx) return FRA_ERR_INVALID;
     FRA_TRY(ctx, cudaSetDevice(ctx->device));
     FRA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    FRA_TRY(ctx, pipe_host_join(ctx));
     return FRA_OK;
 }
 

@@ -63,6 +63,11 @@ typedef enum fra_status {
 #define FRA_K1_FORCE_LANE   0x2u     /* always use the lane-per-channel window+IIR kernel */
 #define FRA_K1_FORCE_STAGE  0x10u    /* always use the warp-per-stage pipeline window+IIR kernel */
 #define FRA_K1_FORCE_DUO    0x20u    /* always use the two-stages-per-warp pipeline window+IIR kernel */
+#define FRA_PIPELINE        0x40u    /* fra_process runs the window+IIR of call i+1 beside the FFT of call i on two
+                                        internal streams (the FPGA does the same: the filter streams the next frame
+                                        while xfft_0 unloads the previous one, dsp_system_top.vhd:530-567).  The call
+                                        only waits for `cuda_stream` (inputs ready); inputs must stay untouched and
+                                        outputs are complete after fra_join() / fra_sync(). */
 #define FRA_K1_FORCE_SPLIT  0x4u     /* always use the stage-per-lane (systolic) window+IIR kernel */
 #define FRA_K1_SPECULATE    0x8u     /* systolic kernel: try the no-overflow recurrence (FFMA->FADD) first and roll a block
                                         back when a sum left the int16 range; same results, measured no faster on B200 */
@@ -173,7 +178,11 @@ int fra_fft_only(fra_ctx *ctx, const int16_t *d_in, int batch, float *d_iq, void
 int fra_profile_enable(fra_ctx *ctx, int on);
 int fra_profile_last(fra_ctx *ctx, float *ms_window_iir, float *ms_fft_pack);
 
-int fra_sync(fra_ctx *ctx);                       /* wait for the context's stream */
+int fra_sync(fra_ctx *ctx);                       /* host waits for everything the context has enqueued */
+/* Device-side join for FRA_PIPELINE contexts: `cuda_stream` waits for all work enqueued by
+ * earlier fra_process calls (no host synchronisation).  A no-op without FRA_PIPELINE, where
+ * fra_process already runs on the caller's stream. */
+int fra_join(fra_ctx *ctx, void *cuda_stream);
 int fra_last_kernel_count(const fra_ctx *ctx);    /* kernels launched by the last fra_process */
 const char *fra_last_cuda_error(const fra_ctx *ctx);
 const char *fra_strerror(int status);

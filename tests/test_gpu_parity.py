@@ -267,3 +267,39 @@ def test_config5_single_stream(fra, rom):
         yw, _ = cg.window_iir(xr[None], rom, 0xA1, g.BANK0_COEFF, B1)
         y, stats = ctx.iir_stream(dev(xr), exact=False)
         assert stats["exact"] == 1 and np.array_equal(y.cpu().numpy(), yw[0])
+
+
+def test_pipeline_mode_matches_sequential(fra, rom):
+    """FRA_PIPELINE: FFT of call i beside window+IIR of call i+1 on internal streams.  Same
+    bits as the sequential context over several continuous frames, state included."""
+    rng = np.random.default_rng(11)
+    c, n, frames = 70, 16384, 5
+    xs = [dev(adversarial(rng, c, n)) for _ in range(frames)]
+    want = []
+    with fra.FraContext(c, n) as ref:
+        ref.command(0x00)
+        for i, x in enumerate(xs):
+            o = ref.process(x, continuous=i > 0, want=("frames", "mag"))
+            want.append((o["frames"].clone(), o["mag"].clone()))
+        st_ref = ref.get_state().clone()
+    with fra.FraContext(c, n, flags=fra._abi.FRA_PIPELINE) as ctx:
+        ctx.command(0x00)
+        got = [ctx.process(x, continuous=i > 0, want=("frames", "mag")) for i, x in enumerate(xs)]
+        ctx.join()
+        torch.cuda.synchronize()
+        for i in range(frames):
+            assert torch.equal(got[i]["frames"], want[i][0]), i
+            assert torch.equal(got[i]["mag"], want[i][1]), i
+        assert torch.equal(ctx.get_state(), st_ref)
+        # caller-owned outputs rewritten every call (filtered + frames): the library orders the
+        # reuse itself; the last frame must equal the oracle continued from the state above
+        y, st = cg.window_iir(xs[0].cpu().numpy(), rom, 0x00, g.BANK0_COEFF, B1, st_ref.cpu().numpy())
+        y2, st2 = cg.window_iir(xs[1].cpu().numpy(), rom, 0x00, g.BANK0_COEFF, B1, st)
+        out = {"filtered": torch.empty((c, n), dtype=torch.int16, device="cuda"),
+               "frames": torch.empty((c, 4 * n), dtype=torch.uint8, device="cuda")}
+        ctx.process(xs[0], continuous=True, want=("filtered", "frames"), out=out)
+        ctx.process(xs[1], continuous=True, want=("filtered", "frames"), out=out)
+        ctx.join()
+        torch.cuda.synchronize()
+        assert np.array_equal(out["filtered"].cpu().numpy(), y2)
+        assert np.array_equal(ctx.get_state().cpu().numpy(), st2)

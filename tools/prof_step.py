@@ -17,13 +17,43 @@ ap.add_argument("--steps", type=int, default=4)
 ap.add_argument("--mode", default="0x00")
 ap.add_argument("--k1", default="auto")
 ap.add_argument("--time", action="store_true")
+ap.add_argument("--pipeline", action="store_true", help="FRA_PIPELINE context; reports whole-loop throughput")
 a = ap.parse_args()
 flags = {"auto": 0, "lane": _abi.FRA_K1_FORCE_LANE, "split": _abi.FRA_K1_FORCE_SPLIT,
          "spec": _abi.FRA_K1_SPECULATE | _abi.FRA_K1_FORCE_SPLIT, "stage": _abi.FRA_K1_FORCE_STAGE, "duo": _abi.FRA_K1_FORCE_DUO}[a.k1]
+if a.pipeline:
+    flags |= _abi.FRA_PIPELINE
 ctx = FraContext(a.channels, a.n, flags=flags)
 ctx.command(int(a.mode, 16))
 xs = [synth.tone_noise(a.channels, a.n, "cuda", frame=i) for i in range(2)]
 out = {"frames": torch.empty((a.channels, 4 * a.n), dtype=torch.uint8, device="cuda")}
+if a.pipeline or a.time:
+    # whole-loop throughput (events on torch's stream; join() makes it wait for the internal streams)
+    xs3 = xs + [synth.tone_noise(a.channels, a.n, "cuda", frame=2)]
+    for i in range(3):
+        ctx.process(xs3[i % 3], want=("frames",), out=out)
+    ctx.sync(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = max(a.steps, 20)
+    e0.record()
+    for i in range(reps):
+        ctx.process(xs3[i % 3], want=("frames",), out=out)
+    ctx.join()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    print(f"channels={a.channels} n={a.n} pipeline={int(a.pipeline)} k1={a.k1}: {ms:.4f} ms/step  "
+          f"{a.channels * a.n / ms / 1e6:.1f} Gs/s over {reps} steps")
+    if a.pipeline:
+        ctx.profile(True)
+        d1, d2 = [], []
+        for i in range(12):
+            ctx.process(xs3[i % 3], want=("frames",), out=out)
+            if i >= 4:
+                t = ctx.profile_last()          # waits for this call's kernels: the next call then starts cold
+                d1.append(t[0]); d2.append(t[1])
+        print(f"  per-kernel durations with a host wait after each call: K1 {min(d1):.4f}  K2 {min(d2):.4f} ms")
+        print("done"); sys.exit(0)
 ctx.profile(True)
 k1, k2 = [], []
 for i in range(a.steps):
