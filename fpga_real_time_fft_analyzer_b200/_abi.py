@@ -63,6 +63,9 @@ SIGNATURES = {
     "fra_window_rom": (C.c_int, [C.POINTER(C.c_int16)]),
     "fra_process": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(FraOutputs), C.c_void_p]),
     "fra_process_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(FraOutputs)]),
+    "fra_process_host_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(FraOutputs),
+                                         C.POINTER(C.c_uint64)]),
+    "fra_host_wait": (C.c_int, [C.c_void_p, C.c_uint64]),
     "fra_get_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "fra_set_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "fra_iir_stream": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int,

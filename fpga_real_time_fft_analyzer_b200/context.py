@@ -31,6 +31,8 @@ class FraContext:
         self._L = lib()
         self._h = C.c_void_p()
         self.channels, self.n, self.device = int(channels), int(fft_size), int(device)
+        self._async_calls = 0
+        self._keep_alive = None
         rc = self._L.fra_create(C.byref(self._h), self.device, self.channels, self.n, flags)
         if rc != _abi.FRA_OK:
             self._h = C.c_void_p()
@@ -169,6 +171,34 @@ class FraContext:
         self._check(self._L.fra_process_host(self._h, x.data_ptr(), int(bool(continuous)), ls, C.byref(o)),
                     "fra_process_host")
         return out
+
+    def process_host_async(self, x, continuous=False, log2_scale=None, want=("frames",)):
+        """process_host without the final wait: returns (outputs, ticket); the outputs (pinned
+        host tensors, two alternating sets) are valid after host_wait(ticket).  x must stay
+        untouched until then.  Two calls may be in flight, so frame i+1 uploads while frame i
+        downloads."""
+        torch = _torch()
+        if isinstance(x, np.ndarray):
+            x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.int16))
+        if x.is_cuda or x.dtype != torch.int16 or not x.is_contiguous() or x.numel() != self.channels * self.n:
+            raise ValueError("x must be a contiguous int16 host array of shape [channels, fft_size]")
+        c, n = self.channels, self.n
+        shapes = {"filtered": ((c, n), torch.int16), "frames": ((c, 4 * n), torch.uint8),
+                  "iq": ((c, n, 2), torch.float32), "mag": ((c, n), torch.float32),
+                  "phase": ((c, n), torch.float32)}
+        slot = self._async_calls & 1
+        self._async_calls += 1
+        out = {k: self.pinned(f"{k}#{slot}", *shapes[k]) for k in want}
+        o = self._outputs_struct(out)
+        ls = _abi.FRA_SCALE_DEFAULT if log2_scale is None else int(log2_scale)
+        ticket = C.c_uint64(0)
+        self._keep_alive = (x, self._keep_alive[0] if getattr(self, "_keep_alive", None) else None)
+        self._check(self._L.fra_process_host_async(self._h, x.data_ptr(), int(bool(continuous)), ls, C.byref(o),
+                                                   C.byref(ticket)), "fra_process_host_async")
+        return out, ticket.value
+
+    def host_wait(self, ticket):
+        self._check(self._L.fra_host_wait(self._h, C.c_uint64(int(ticket))), "fra_host_wait")
 
     def get_state(self):
         torch = _torch()

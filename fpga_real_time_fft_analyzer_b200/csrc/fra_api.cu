@@ -72,6 +72,9 @@ struct fra_ctx {
     cudaStream_t pipe_k1 = nullptr, pipe_k2 = nullptr;
     cudaEvent_t pipe_in = nullptr, pipe_k1_done[2] = {nullptr, nullptr}, pipe_k2_done[2] = {nullptr, nullptr};
     unsigned long long pipe_calls = 0;
+    // fra_process_host_async: completion events per call slot (two calls in flight) and copy stream
+    cudaEvent_t host_done[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+    unsigned long long host_calls = 0;
     size_t scratch_elems = 0;         // int16 elements allocated at d_scratch
 
     bool profiling = false;
@@ -304,6 +307,15 @@ cudaError_t pipe_host_join(fra_ctx *ctx)
     return e;
 }
 
+// host waits for the copy streams (calls of fra_process_host_async still in flight)
+cudaError_t host_streams_join(fra_ctx *ctx)
+{
+    cudaError_t e = cudaSuccess;
+    for (auto st : ctx->copy_streams)
+        if (st && e == cudaSuccess) e = cudaStreamSynchronize(st);
+    return e;
+}
+
 fra_outputs offset_outputs(const fra_outputs &o, size_t c0, int n)
 {
     fra_outputs r = o;
@@ -412,6 +424,10 @@ int fra_destroy(fra_ctx *ctx)
     if (!ctx) return FRA_ERR_INVALID;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    host_streams_join(ctx);
+    for (auto &slot : ctx->host_done)
+        for (cudaEvent_t e : slot)
+            if (e) cudaEventDestroy(e);
     for (cudaStream_t ps : {ctx->pipe_k1, ctx->pipe_k2})
         if (ps) { cudaStreamSynchronize(ps); cudaStreamDestroy(ps); }
     for (cudaEvent_t pe : {ctx->pipe_in, ctx->pipe_k1_done[0], ctx->pipe_k1_done[1], ctx->pipe_k2_done[0], ctx->pipe_k2_done[1]})
@@ -485,6 +501,8 @@ int fra_reset(fra_ctx *ctx)
     if (!ctx) return FRA_ERR_INVALID;
     do_reset(ctx);
     FRA_TRY(ctx, cudaSetDevice(ctx->device));
+    FRA_TRY(ctx, pipe_host_join(ctx));
+    FRA_TRY(ctx, host_streams_join(ctx));
     // synchronous: a reset must be ordered before work on ANY stream the caller uses next
     FRA_TRY(ctx, cudaMemsetAsync(ctx->d_state, 0, (size_t)ctx->channels * 24 * sizeof(int16_t), ctx->stream));
     FRA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -580,7 +598,26 @@ int fra_join(fra_ctx *ctx, void *cuda_stream)
 
 int fra_process_host(fra_ctx *ctx, const int16_t *h_in, int continuous, int log2_scale, const fra_outputs *h_out)
 {
-    if (!ctx || !h_in || !h_out) return FRA_ERR_INVALID;
+    uint64_t ticket = 0;
+    int rc = fra_process_host_async(ctx, h_in, continuous, log2_scale, h_out, &ticket);
+    if (rc != FRA_OK) return rc;
+    return fra_host_wait(ctx, ticket);
+}
+
+int fra_host_wait(fra_ctx *ctx, uint64_t ticket)
+{
+    if (!ctx || ticket == 0 || ticket > ctx->host_calls) return FRA_ERR_INVALID;
+    if (ticket + 2 <= ctx->host_calls) return FRA_OK;          // its slot was waited for when it was reused
+    FRA_TRY(ctx, cudaSetDevice(ctx->device));
+    for (cudaEvent_t e : ctx->host_done[ticket & 1])
+        if (e) FRA_TRY(ctx, cudaEventSynchronize(e));
+    return FRA_OK;
+}
+
+int fra_process_host_async(fra_ctx *ctx, const int16_t *h_in, int continuous, int log2_scale,
+                           const fra_outputs *h_out, uint64_t *ticket)
+{
+    if (!ctx || !h_in || !h_out || !ticket) return FRA_ERR_INVALID;
     FRA_TRY(ctx, pipe_host_join(ctx));
     if (log2_scale == FRA_SCALE_DEFAULT) log2_scale = -ctx->log2n;
     if (log2_scale < -40 || log2_scale > 16) return FRA_ERR_INVALID;
@@ -633,11 +670,21 @@ int fra_process_host(fra_ctx *ctx, const int16_t *h_in, int continuous, int log2
         if (h_out->d_phase)
             FRA_TRY(ctx, cudaMemcpyAsync(h_out->d_phase + c0 * n, o.d_phase, nch * n * 4, cudaMemcpyDeviceToHost, st));
     }
-    for (auto st : ctx->copy_streams) {
-        cudaError_t e = cudaStreamSynchronize(st);
-        if (e != cudaSuccess && rc == FRA_OK) rc = fail_cuda(ctx, e, "cudaStreamSynchronize");
+    if (rc != FRA_OK) {
+        host_streams_join(ctx);
+        return rc;
     }
-    return rc;
+    // completion of THIS call on every copy stream; at most two calls are in flight
+    const unsigned long long id = ctx->host_calls + 1;
+    for (int s = 0; s < 3; ++s) {
+        cudaEvent_t &e = ctx->host_done[id & 1][s];
+        if (!e) FRA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        else FRA_TRY(ctx, cudaEventSynchronize(e));           // the call two before this one
+        FRA_TRY(ctx, cudaEventRecord(e, ctx->copy_streams[s]));
+    }
+    ctx->host_calls = id;
+    *ticket = id;
+    return FRA_OK;
 }
 
 int fra_get_state(fra_ctx *ctx, int16_t *d_state, void *cuda_stream)
@@ -645,6 +692,7 @@ int fra_get_state(fra_ctx *ctx, int16_t *d_state, void *cuda_stream)
     if (!ctx || !d_state) return FRA_ERR_INVALID;
     FRA_TRY(ctx, cudaSetDevice(ctx->device));
     FRA_TRY(ctx, pipe_host_join(ctx));                 // FRA_PIPELINE: the state belongs to pipe_k1 until it drains
+    FRA_TRY(ctx, host_streams_join(ctx));              // ... or to an asynchronous host call
     cudaStream_t st = (cudaStream_t)cuda_stream;      // NULL = the legacy default stream
     FRA_TRY(ctx, cudaMemcpyAsync(d_state, ctx->d_state, (size_t)ctx->channels * 24 * sizeof(int16_t),
                                  cudaMemcpyDeviceToDevice, st));
@@ -656,6 +704,7 @@ int fra_set_state(fra_ctx *ctx, const int16_t *d_state, void *cuda_stream)
     if (!ctx || !d_state) return FRA_ERR_INVALID;
     FRA_TRY(ctx, cudaSetDevice(ctx->device));
     FRA_TRY(ctx, pipe_host_join(ctx));                 // FRA_PIPELINE: the state belongs to pipe_k1 until it drains
+    FRA_TRY(ctx, host_streams_join(ctx));              // ... or to an asynchronous host call
     cudaStream_t st = (cudaStream_t)cuda_stream;      // NULL = the legacy default stream
     FRA_TRY(ctx, cudaMemcpyAsync(ctx->d_state, d_state, (size_t)ctx->channels * 24 * sizeof(int16_t),
                                  cudaMemcpyDeviceToDevice, st));
@@ -915,6 +964,7 @@ int fra_sync(fra_ctx *ctx)
     FRA_TRY(ctx, cudaSetDevice(ctx->device));
     FRA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     FRA_TRY(ctx, pipe_host_join(ctx));
+    FRA_TRY(ctx, host_streams_join(ctx));
     return FRA_OK;
 }
 

@@ -134,6 +134,18 @@ int fra_process(fra_ctx *ctx, const int16_t *d_in, int continuous, int log2_scal
 int fra_process_host(fra_ctx *ctx, const int16_t *h_in, int continuous, int log2_scale,
                      const fra_outputs *h_out);
 
+/* The same without the final wait: everything (H2D, kernels, D2H) is enqueued on the context's
+ * copy streams and *ticket identifies the call; fra_host_wait(ctx, ticket) blocks until its
+ * outputs are in host memory.  Two calls may be in flight (a third waits for the first), so a
+ * receiver loop uploads frame i+1 while frame i is still downloading - PCIe is full duplex and
+ * the D2H side (4 B per sample) is the longer one.  The caller keeps h_in and the buffers in
+ * *h_out untouched until the wait returns, i.e. alternates two sets of host buffers.
+ * (UdpReceiver / UartReceiver do the same with their byte buffers while a frame is decoded,
+ * scripts/fft_analyzer_gui.py:373-455.) */
+int fra_process_host_async(fra_ctx *ctx, const int16_t *h_in, int continuous, int log2_scale,
+                           const struct fra_outputs *h_out, uint64_t *ticket);
+int fra_host_wait(fra_ctx *ctx, uint64_t ticket);
+
 /* IIR history, [C][6][4] int16 = per stage (x[n-1], x[n-2], y[n-1], y[n-2])
  * (registers ve(1..2), vs(1..2) of NEW/filter_iir_cust.vhd:45-46). Device pointers. */
 int fra_get_state(fra_ctx *ctx, int16_t *d_state, void *cuda_stream);

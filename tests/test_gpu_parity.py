@@ -303,3 +303,31 @@ def test_pipeline_mode_matches_sequential(fra, rom):
         torch.cuda.synchronize()
         assert np.array_equal(out["filtered"].cpu().numpy(), y2)
         assert np.array_equal(ctx.get_state().cpu().numpy(), st2)
+
+
+def test_process_host_async_matches_sync(fra, rom):
+    """Two host calls in flight (upload of frame i+1 beside the download of frame i): same
+    bytes as the synchronous call, history carried across the calls."""
+    rng = np.random.default_rng(12)
+    c, n, frames = 1024, 16384, 4            # 2^24 samples: the sliced, three-stream path
+    xs = [torch.from_numpy(adversarial(rng, c, n)).pin_memory() for _ in range(frames)]
+    with fra.FraContext(c, n) as ref, fra.FraContext(c, n) as ctx:
+        ref.command(0x00)
+        ctx.command(0x00)
+        pending = None
+        for i, x in enumerate(xs):
+            w = {k: v.clone() for k, v in ref.process_host(x, continuous=i > 0, want=("frames", "filtered")).items()}
+            cur = ctx.process_host_async(x, continuous=i > 0, want=("frames", "filtered")) + (w,)
+            if pending is not None:
+                ctx.host_wait(pending[1])
+                for k in ("frames", "filtered"):
+                    assert torch.equal(pending[0][k], pending[2][k]), (i - 1, k)
+            pending = cur
+        ctx.host_wait(pending[1])
+        for k in ("frames", "filtered"):
+            assert torch.equal(pending[0][k], pending[2][k]), ("last", k)
+        assert torch.equal(ctx.get_state(), ref.get_state())
+    y, st = None, None
+    for x in xs:
+        y, st = cg.window_iir(x.numpy()[:8], rom, 0x00, g.BANK0_COEFF, B1, st)
+    assert np.array_equal(pending[0]["filtered"].numpy()[:8], y)
