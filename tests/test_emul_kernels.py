@@ -51,6 +51,27 @@ def test_k1_bit_exact_with_state_and_reload(flags, name, channels, rom):
         f.close()
 
 
+def test_pipeline_flag_same_results(rom):
+    """FRA_PIPELINE only changes which streams the kernels go to: the host logic around it
+    (two scratch buffers, hand-over events) must leave results and state unchanged."""
+    rng = np.random.default_rng(5)
+    c, n = 6, 1024
+    f = EmulFra(c, n, _abi.FRA_PIPELINE)
+    try:
+        f.command(bytes([0x00]))
+        st = None
+        for frame in range(3):
+            x = adversarial(rng, c, n)
+            y, st = cg.window_iir(x, rom, 0x00, g.BANK0_COEFF, B1, st)
+            out = f.process(x, continuous=frame > 0, want=("filtered", "frames"))
+            assert np.array_equal(out["filtered"], y)
+            out2 = f.process(x, continuous=False, want=("frames",))       # library-owned scratch, alternating
+            y0, st = cg.window_iir(x, rom, 0x00, g.BANK0_COEFF, B1, None)
+            assert np.array_equal(f.get_state(), st)
+    finally:
+        f.close()
+
+
 def test_k1_random_coefficients_and_user_state(rom):
     rng = np.random.default_rng(7)
     n, c = 1024, 7
