@@ -28,7 +28,8 @@ for log2n in range(10, 16):
     batch = (1 << 26) // N
     with FraContext(batch, N) as ctx:
         xs = synth.full_range(batch, N, dev)
-        ctx.fft_only(xs)
+        for _ in range(3):                 # warm-up: module load, and the caching allocator gets both output blocks
+            out = ctx.fft_only(xs)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         e0.record()
