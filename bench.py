@@ -286,7 +286,7 @@ def run_ours(args):
                 kernels[name] = {"ms": ms, "achieved_gbs": ach, "frac": ach / peak,
                                  "alg_bytes_per_sample": B_ALG[name]}
         dom = "window_iir" if k1 >= k2 else "fft_pack"
-        roofline = {"bound": "hbm", "kernel": ("k1_duo<true,true>" if dom == "window_iir" else "k2_fft<14,false,0,0>"),
+        roofline = {"bound": "hbm", "kernel": ("k1_duo<true,true,true>" if dom == "window_iir" else "k2_fft<14,false,0,0>"),
                     "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                     "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
                     "kernels": kernels, "sequential_ms_per_step": k1 + k2,

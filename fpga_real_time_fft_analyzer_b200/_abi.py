@@ -54,6 +54,8 @@ SIGNATURES = {
     "fra_destroy": (C.c_int, [C.c_void_p]),
     "fra_command": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),
     "fra_load_bank1": (C.c_int, [C.c_void_p, C.POINTER(C.c_int8)]),
+    "fra_load_sections": (C.c_int, [C.c_void_p, C.POINTER(C.c_int8)]),
+    "fra_get_sections": (C.c_int, [C.c_void_p, C.POINTER(C.c_int8)]),
     "fra_set_mode": (C.c_int, [C.c_void_p, C.c_uint8]),
     "fra_reset": (C.c_int, [C.c_void_p]),
     "fra_get_mode": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint8)]),

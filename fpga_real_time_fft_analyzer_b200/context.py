@@ -78,6 +78,18 @@ class FraContext:
         arr = (C.c_int8 * 12)(*[int(v) for v in np.asarray(coeff12).reshape(12)])
         self._check(self._L.fra_load_bank1(self._h, arr), "fra_load_bank1")
 
+    def load_sections(self, coeff6x6):
+        """Six independent sections (int8 [6][6], RTL register order B0,B1,B2,A0,A1,A2): a
+        superset of the 12-byte bank; becomes bank 1 until the next 12-byte upload."""
+        arr = (C.c_int8 * 36)(*[int(v) for v in np.asarray(coeff6x6).reshape(36)])
+        self._check(self._L.fra_load_sections(self._h, arr), "fra_load_sections")
+
+    def sections(self):
+        """int8 [6][6]: the coefficients the current mode filters with."""
+        arr = (C.c_int8 * 36)()
+        self._check(self._L.fra_get_sections(self._h, arr), "fra_get_sections")
+        return np.array(arr[:], dtype=np.int8).reshape(6, 6)
+
     def set_mode(self, mode: int):
         self._check(self._L.fra_set_mode(self._h, mode), "fra_set_mode")
 

@@ -46,6 +46,8 @@ struct fra_ctx {
     uint8_t mode = FRA_MODE_BYPASS;
     uint8_t transport = FRA_CMD_ETHERNET_MODE;
     int8_t bank1[12] = {0};
+    int8_t sections[6][6] = {{0}};  // fra_load_sections: six independent sections (superset of the 12-byte bank)
+    bool sections_loaded = false;   // bank 1 is `sections` instead of `bank1` alternated
     int upload_pos = -1;            // >= 0: inside a 0xF1 upload, bytes received so far
     int8_t upload_buf[12] = {0};
     uint64_t n_start = 0, n_request = 0, n_reset = 0, n_upload = 0;
@@ -112,11 +114,35 @@ StageCoef make_stage(const int8_t *k)       // k = B0,B1,B2,A0,A1 (NEW/filter_ii
     return c;
 }
 
-CascadeCoef make_cascade(const int8_t coeff12[12])
+struct Sections {
+    int8_t c[kStages][6];    // B0,B1,B2,A0,A1,A2 per stage
+};
+
+// the 12-byte bank as the RTL wires it: ALPHA (bytes 0..5) -> stages 1,3,5, BETA (bytes 6..11) -> stages 2,4,6
+// (NEW/filter_iir12_cust.vhd:68-240; bytes 5 and 11 = A2 are unconnected)
+Sections alternate(const int8_t coeff12[12])
+{
+    Sections s;
+    for (int i = 0; i < kStages; ++i) std::memcpy(s.c[i], coeff12 + 6 * (i & 1), 6);
+    return s;
+}
+
+// the coefficients the current mode filters with
+Sections current_sections(const fra_ctx *ctx)
+{
+    if (ctx->mode == FRA_MODE_BANK1) {
+        if (!ctx->sections_loaded) return alternate(ctx->bank1);
+        Sections s;
+        std::memcpy(s.c, ctx->sections, sizeof(s.c));
+        return s;
+    }
+    return alternate(kBank0);
+}
+
+CascadeCoef make_cascade(const Sections &s)
 {
     CascadeCoef c;
-    c.set[0] = make_stage(coeff12);          // ALPHA: bytes 0..4
-    c.set[1] = make_stage(coeff12 + 6);      // BETA: bytes 6..10 (bytes 5, 11 = A2 are unconnected)
+    for (int i = 0; i < kStages; ++i) c.set[i] = make_stage(s.c[i]);
     return c;
 }
 
@@ -125,6 +151,8 @@ void do_reset(fra_ctx *ctx)
     // rst_n pulse: NEW/command_control.vhd:50, NEW/filter_iir12_cust.vhd:51-52, IMP/sequ2.vhd:86
     ctx->mode = FRA_MODE_BYPASS;
     std::memset(ctx->bank1, 0, sizeof(ctx->bank1));
+    std::memset(ctx->sections, 0, sizeof(ctx->sections));
+    ctx->sections_loaded = false;
     ctx->transport = FRA_CMD_ETHERNET_MODE;
     ctx->n_reset++;
 }
@@ -194,7 +222,8 @@ int process_range(fra_ctx *ctx, const int16_t *d_in, int c0, int nch, int contin
         k1.out = filt;
         k1.state = ctx->d_state + (size_t)c0 * 24;
         k1.rom32 = ctx->d_rom32;
-        k1.coef = make_cascade(ctx->mode == FRA_MODE_BANK0 ? kBank0 : ctx->bank1);
+        const Sections sec = current_sections(ctx);
+        k1.coef = make_cascade(sec);
         k1.channels = nch;
         k1.n = n;
         k1.continuous = continuous;
@@ -207,14 +236,19 @@ int process_range(fra_ctx *ctx, const int16_t *d_in, int c0, int nch, int contin
         if (ctx->flags & FRA_K1_FORCE_SPLIT) variant = 1;
         if (ctx->flags & FRA_K1_FORCE_STAGE) variant = 2;
         if (ctx->flags & FRA_K1_FORCE_DUO) variant = 3;
-        const int8_t *bank = (ctx->mode == FRA_MODE_BANK0) ? kBank0 : ctx->bank1;
-        const bool b1z = bank[1] == 0 && bank[7] == 0;          // x[n-1] coefficient zero in both sets: skip that product
+        bool b1z = true, fast = true;
+        for (int i = 0; i < kStages; ++i) {
+            b1z = b1z && sec.c[i][1] == 0;                       // x[n-1] coefficient zero in every stage: skip that product
+            fast = fast && std::abs((int)sec.c[i][4]) <= kFastMaxA1;   // two-instruction recurrence (fra_common.cuh)
+        }
         if (variant == 3) {
             const int grid = (nch + 31) / 32;
-            // two-instruction recurrence when both y[n-1] coefficients are small enough (fra_common.cuh)
-            const bool fast = std::abs((int)bank[4]) <= kFastMaxA1 && std::abs((int)bank[10]) <= kFastMaxA1;
-            auto kfn = fast ? (b1z ? k1_duo<true, true> : k1_duo<false, true>)
-                            : (b1z ? k1_duo<true, false> : k1_duo<false, false>);
+            bool alt = true;                                       // ALPHA, BETA, ALPHA, BETA, ALPHA, BETA
+            for (int i = 2; i < kStages; ++i) alt = alt && std::memcmp(sec.c[i], sec.c[i & 1], 5) == 0;
+            void (*const table[8])(K1Args) = {
+                k1_duo<false, false, false>, k1_duo<true, false, false>, k1_duo<false, true, false>, k1_duo<true, true, false>,
+                k1_duo<false, false, true>,  k1_duo<true, false, true>,  k1_duo<false, true, true>,  k1_duo<true, true, true>};
+            auto kfn = table[(b1z ? 1 : 0) | (fast ? 2 : 0) | (alt ? 4 : 0)];
             static_assert(kDuoSmemRequest >= kDuoSmemBytes, "k1_duo shared memory");
             FRA_TRY(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kDuoSmemRequest));
             FRA_LAUNCH(kfn, dim3(grid), dim3(kDuoWarps * 32), (size_t)kDuoSmemRequest, st, k1);
@@ -455,6 +489,7 @@ int fra_command(fra_ctx *ctx, const uint8_t *bytes, size_t n)
             ctx->upload_buf[ctx->upload_pos++] = (int8_t)b;
             if (ctx->upload_pos == 12) {
                 std::memcpy(ctx->bank1, ctx->upload_buf, 12);
+                ctx->sections_loaded = false;
                 ctx->upload_pos = -1;
                 ctx->n_upload++;
             }
@@ -484,7 +519,25 @@ int fra_load_bank1(fra_ctx *ctx, const int8_t coeff[12])
 {
     if (!ctx || !coeff) return FRA_ERR_INVALID;
     std::memcpy(ctx->bank1, coeff, 12);
+    ctx->sections_loaded = false;
     ctx->n_upload++;
+    return FRA_OK;
+}
+
+int fra_load_sections(fra_ctx *ctx, const int8_t coeff[36])
+{
+    if (!ctx || !coeff) return FRA_ERR_INVALID;
+    std::memcpy(ctx->sections, coeff, 36);
+    ctx->sections_loaded = true;
+    ctx->n_upload++;
+    return FRA_OK;
+}
+
+int fra_get_sections(const fra_ctx *ctx, int8_t coeff[36])
+{
+    if (!ctx || !coeff) return FRA_ERR_INVALID;
+    const Sections s = current_sections(ctx);
+    std::memcpy(coeff, s.c, 36);
     return FRA_OK;
 }
 
@@ -719,14 +772,14 @@ int fra_iir_stream(fra_ctx *ctx, const int16_t *d_in, int16_t *d_out, size_t n, 
     FRA_TRY(ctx, pipe_host_join(ctx));
     cudaStream_t st = ctx->stream;
     const bool iir = (ctx->mode == FRA_MODE_BANK0 || ctx->mode == FRA_MODE_BANK1);
-    const int8_t *bank = (ctx->mode == FRA_MODE_BANK1) ? ctx->bank1 : kBank0;
+    const Sections sec = current_sections(ctx);
     fra_stream_stats s = {0, 0, 0, 0, 0, 0};
 
     // pole radius of z^2 + (A1/128) z + A0/128 (both sets): the block scan needs a stable cascade
     double r = 0.0;
     if (iir && !exact) {
-        for (int set = 0; set < 2; ++set) {
-            const double a0 = bank[6 * set + 3] / 128.0, a1 = bank[6 * set + 4] / 128.0;
+        for (int set = 0; set < kStages; ++set) {
+            const double a0 = sec.c[set][3] / 128.0, a1 = sec.c[set][4] / 128.0;
             const double disc = a1 * a1 - 4.0 * a0;
             const double rs = disc < 0.0 ? std::sqrt(a0)
                                          : std::max(std::fabs((-a1 + std::sqrt(disc)) / 2.0), std::fabs((-a1 - std::sqrt(disc)) / 2.0));
@@ -744,7 +797,7 @@ int fra_iir_stream(fra_ctx *ctx, const int16_t *d_in, int16_t *d_out, size_t n, 
         k1.out = d_out;
         k1.state = ctx->d_state;
         k1.rom32 = ctx->d_rom32;
-        k1.coef = make_cascade(bank);
+        k1.coef = make_cascade(sec);
         k1.channels = 1;
         k1.n = (int)n;
         k1.continuous = continuous;
@@ -792,7 +845,7 @@ int fra_iir_stream(fra_ctx *ctx, const int16_t *d_in, int16_t *d_out, size_t n, 
     a.in = d_in;
     a.out = d_out;
     a.rom32 = ctx->d_rom32;
-    a.coef = make_cascade(bank);
+    a.coef = make_cascade(sec);
     a.entry = ctx->d_entry;
     a.exit_ = ctx->d_exit;
     a.state0 = ctx->d_state;
@@ -816,7 +869,7 @@ int fra_iir_stream(fra_ctx *ctx, const int16_t *d_in, int16_t *d_out, size_t n, 
         auto step = [&](const double *in, double *out) {           // u = 0
             double v = 0.0;
             for (int sg = 0; sg < kStages; ++sg) {
-                const StageCoef &k = cc.set[sg & 1];
+                const StageCoef &k = cc.set[sg];
                 const double x1 = in[4 * sg], x2 = in[4 * sg + 1], y1 = in[4 * sg + 2], y2 = in[4 * sg + 3];
                 const double y = (double)k.b2 * v + (double)k.b1 * x1 + (double)k.b0 * x2 + (double)k.na0 * y2 + (double)k.na1 * y1;
                 out[4 * sg] = v; out[4 * sg + 1] = x1; out[4 * sg + 2] = y; out[4 * sg + 3] = y1;

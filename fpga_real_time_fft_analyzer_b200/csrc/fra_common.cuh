@@ -50,7 +50,7 @@ struct StageCoef {
 constexpr int kFastMaxA1 = 60;
 
 struct CascadeCoef {
-    StageCoef set[2];    // set 0 (ALPHA): stages 1,3,5; set 1 (BETA): stages 2,4,6
+    StageCoef set[kStages];   // one per stage; the 12-byte protocol fills them ALPHA, BETA, ALPHA, ... (stages 1,3,5 / 2,4,6)
 };
 
 struct StageState {      // registers ve(1), ve(2), vs(1), vs(2) as exact floats

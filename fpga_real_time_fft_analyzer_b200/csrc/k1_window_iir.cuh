@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(kLaneBlock) k1_lane(K1Args a)
                 float v = small_int_to_float(window_int(x, rom[j]));
 #pragma unroll
                 for (int s = 0; s < kStages; ++s)
-                    acc[j] = biquad_step<B1Z>(v, a.coef.set[s & 1], st[s], &v);
+                    acc[j] = biquad_step<B1Z>(v, a.coef.set[s], st[s], &v);
             }
             ow[2 * q] = pack16_acc(acc[0], acc[1]);
             ow[2 * q + 1] = pack16_acc(acc[2], acc[3]);
@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(kSplitWarps * 32) k1_split(K1Args a)
     L.s = lane - g_raw * kStages;
     L.first = (L.s == 0);
     L.last = (L.s == kStages - 1);
-    L.k = a.coef.set[L.s & 1];
+    L.k = a.coef.set[L.s];
     L.y = 0.0f;
 #pragma unroll
     for (int j = 0; j < kSkew - 1; ++j) L.up[j] = 0.0f;
@@ -554,7 +554,7 @@ __global__ void __launch_bounds__(kStageWarps * 32, 2) k1_stage(K1Args a)
         }
     } else {
         const int s = warp - 1;
-        const StageCoef k = a.coef.set[s & 1];
+        const StageCoef k = a.coef.set[s];
         StageState st = {0.0f, 0.0f, 0.0f, 0.0f};
         if (a.continuous) {
             const uint2 v = __ldg(reinterpret_cast<const uint2 *>(a.state + ((size_t)cc * kStages + s) * 4));
@@ -787,7 +787,10 @@ FRA_DEV void duo_store_state(const K1Args &a, int c, int s, const StageState &st
     *reinterpret_cast<uint2 *>(a.state + ((size_t)c * kStages + s) * 4) = v;
 }
 
-template <bool B1Z, bool FAST>
+// ALT: the six stages use two alternating coefficient sets (the RTL's bank layout): the pair's
+// coefficients are then compile-time addresses and stay in uniform registers (a run-time set index
+// moves them to vector registers and costs 5 %)
+template <bool B1Z, bool FAST, bool ALT>
 __global__ void __launch_bounds__(kDuoWarps * 32, 2) k1_duo(K1Args a)
 {
     FRA_DYN_SMEM(smem_raw);
@@ -817,7 +820,7 @@ __global__ void __launch_bounds__(kDuoWarps * 32, 2) k1_duo(K1Args a)
         }
     } else {
         const int p = warp - 1;                                  // stage pair: stages 2p and 2p+1
-        const StageCoef ka = a.coef.set[0], kb = a.coef.set[1];
+        const StageCoef ka = a.coef.set[ALT ? 0 : 2 * p], kb = a.coef.set[ALT ? 1 : 2 * p + 1];
         StageState sa = duo_load_state(a, cc, 2 * p), sb = duo_load_state(a, cc, 2 * p + 1);
         float ua = sa.y1 + kBias16, ub = sb.y1 + kBias16;
         for (int t = 0; t < n_steps; ++t) {

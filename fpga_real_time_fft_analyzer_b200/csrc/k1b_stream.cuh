@@ -108,7 +108,9 @@ FRA_DEV float stage_bias(const StageCoef &k)
 template <int MODE>
 FRA_DEV void stream_run(const K1bArgs &a, StageState (&st)[kStages], unsigned long long begin, unsigned long long end)
 {
-    const float bias0 = stage_bias(a.coef.set[0]), bias1 = stage_bias(a.coef.set[1]);
+    float bias[kStages];
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) bias[s] = stage_bias(a.coef.set[s]);
     for (unsigned long long n0 = begin; n0 < end; n0 += 8) {
         const uint4 xv = ldg128(a.in + n0);
         const unsigned xw[4] = {xv.x, xv.y, xv.z, xv.w};
@@ -126,10 +128,10 @@ FRA_DEV void stream_run(const K1bArgs &a, StageState (&st)[kStages], unsigned lo
                 if (a.iir) {
                     if (MODE == 2) {
 #pragma unroll
-                        for (int s = 0; s < kStages; ++s) v = biquad_linear(v, a.coef.set[s & 1], st[s], (s & 1) ? bias1 : bias0);
+                        for (int s = 0; s < kStages; ++s) v = biquad_linear(v, a.coef.set[s], st[s], bias[s]);
                     } else {
 #pragma unroll
-                        for (int s = 0; s < kStages; ++s) acc = biquad_step(v, a.coef.set[s & 1], st[s], &v);
+                        for (int s = 0; s < kStages; ++s) acc = biquad_step(v, a.coef.set[s], st[s], &v);
                     }
                 }
                 acc2[e] = acc;

@@ -81,6 +81,22 @@ class GpuReceiver:
             print(f"Filter coefficient send error: {e}")
             return False
 
+    def send_filter_sections(self, sections) -> bool:
+        """Superset of send_filter_coefficients: 1..6 independent
+        sections of int8 bytes in the RTL's register order B0,B1,B2,A0,A1,A2, e.g. from
+        filter_design.quantize_sections(sos, rtl_compatible=True).  Goes through the 0xF1 byte
+        protocol when the design fits the RTL's two alternating sets."""
+        try:
+            if not self.active:
+                return False
+            from . import filter_design
+            how = filter_design.upload(self.ctx, sections, select=False)
+            print(f"Sent filter sections ({how})")
+            return True
+        except Exception as e:
+            print(f"Filter section send error: {e}")
+            return False
+
     def send_start_sequence(self) -> bool:                             # GUI:529-541: 0x55 then 0xA5
         return self._send_raw(_abi.START_COMMAND) and self.send_data_request()
 

@@ -93,7 +93,17 @@ int fra_destroy(fra_ctx *ctx);
 int fra_command(fra_ctx *ctx, const uint8_t *bytes, size_t n);
 
 /* Same effects without the byte stream. */
-int fra_load_bank1(fra_ctx *ctx, const int8_t coeff[12]);  /* 0xF1 payload: B0,B1,B2,A0,A1,A2 x {set0,set1}, NEW/filter_iir12_cust.vhd:83-94 */
+int fra_load_bank1(fra_ctx *ctx, const int8_t coeff[12]);
+
+/* Superset of the 12-byte protocol: six INDEPENDENT sections, 6 bytes
+ * each in the RTL's register order B0,B1,B2,A0,A1,A2 (B2 -> x[n], B1 -> x[n-1], B0 -> x[n-2],
+ * A1 -> y[n-1], A0 -> y[n-2], A2 unconnected; products >> 7), stage 1 first.  Becomes bank 1
+ * (mode 0xA1) until the next 0xF1 upload / fra_load_bank1, which restores the RTL's two
+ * alternating sets (filter_iir12_cust.vhd:68-240).  Takes effect at the next frame boundary;
+ * the IIR history is kept.  fra_get_sections returns the 36 bytes the CURRENT mode filters with
+ * (bank 0 and 12-byte uploads expanded ALPHA, BETA, ALPHA, ...). */
+int fra_load_sections(fra_ctx *ctx, const int8_t coeff[36]);
+int fra_get_sections(const fra_ctx *ctx, int8_t coeff[36]);  /* 0xF1 payload: B0,B1,B2,A0,A1,A2 x {set0,set1}, NEW/filter_iir12_cust.vhd:83-94 */
 int fra_set_mode(fra_ctx *ctx, uint8_t mode);              /* 0x00 | 0xA1 | 0xB1, NEW/command_control.vhd:53-58 */
 int fra_reset(fra_ctx *ctx);                               /* 0xFF: history 0, bank 1 = 0, mode 0xB1, window address 0 */
 

@@ -56,6 +56,23 @@ def window_iir(x, rom, mode, bank0, bank1, state=None, start=0):
     return y, st
 
 
+def window_iir_sections(x, rom, coeff6x6, state=None, start=0):
+    """Window, then six independent sections (int8 [6][6]): x int16 [C, T] -> (y, state)."""
+    x = np.ascontiguousarray(x, dtype=np.int16)
+    c, t = x.shape
+    w = np.empty_like(x)
+    y = np.empty_like(x)
+    rom = np.ascontiguousarray(rom, dtype=np.int16)
+    k = np.ascontiguousarray(coeff6x6, dtype=np.int8).reshape(36)
+    st = (np.zeros((c, 6, 4), dtype=np.int16) if state is None
+          else np.ascontiguousarray(state, dtype=np.int16).copy())
+    lib().gold_window(_p(x, ctypes.c_int16), _p(w, ctypes.c_int16), ctypes.c_size_t(c), ctypes.c_size_t(t),
+                      _p(rom, ctypes.c_int16), ctypes.c_size_t(len(rom)), ctypes.c_size_t(start))
+    lib().gold_iir_sections(_p(w, ctypes.c_int16), _p(y, ctypes.c_int16), ctypes.c_size_t(c), ctypes.c_size_t(t),
+                            _p(k, ctypes.c_int8), _p(st, ctypes.c_int16))
+    return y, st
+
+
 def iir12(x, coeff12, state=None):
     x = np.ascontiguousarray(x, dtype=np.int16)
     c, t = x.shape

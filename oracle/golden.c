@@ -74,6 +74,30 @@ void gold_iir12(const int16_t *x, int16_t *y, size_t channels, size_t t,
     }
 }
 
+/* Superset used by SURVEY section 8 row f3: six INDEPENDENT sections, 6 bytes each in the same
+ * register order (B0,B1,B2,A0,A1,A2; A2 unconnected).  The per-stage arithmetic is the one of
+ * gold_iir12 (NEW/filter_iir_cust.vhd:96-118); only the coefficient routing differs. */
+void gold_iir_sections(const int16_t *x, int16_t *y, size_t channels, size_t t,
+                       const int8_t coeff36[36], int16_t *state)
+{
+    for (size_t c = 0; c < channels; ++c) {
+        int16_t *st = state + c * 24;
+        for (size_t n = 0; n < t; ++n) {
+            int32_t v = x[c * t + n];
+            for (int s = 0; s < 6; ++s) {
+                const int8_t *k = coeff36 + 6 * s;
+                int16_t *q = st + 4 * s;                 /* x1 x2 y1 y2 */
+                int32_t yn = wrap16(slice_T(v, k[2]) + slice_T(q[0], k[1]) + slice_T(q[1], k[0])
+                                    - slice_T(q[3], k[3]) - slice_T(q[2], k[4]));
+                q[1] = q[0]; q[0] = (int16_t)v;
+                q[3] = q[2]; q[2] = (int16_t)yn;
+                v = yn;
+            }
+            y[c * t + n] = (int16_t)v;
+        }
+    }
+}
+
 /* window followed by the selected path (NEW/command_control.vhd:90-116):
  * mode 0x00 -> bank0, 0xA1 -> bank1, else bypass.  state may be NULL in bypass. */
 void gold_window_iir(const int16_t *x, int16_t *y, size_t channels, size_t t,

@@ -160,6 +160,23 @@ def iir12(x: np.ndarray, coeff12, state: np.ndarray | None = None):
     return v, new_state
 
 
+def iir_sections(x: np.ndarray, coeff6x6, state: np.ndarray | None = None):
+    """Superset of iir12: six INDEPENDENT sections, int8 [6][6] in the
+    RTL's register order B0,B1,B2,A0,A1,A2 (A2 unconnected); same per-stage arithmetic
+    (NEW/filter_iir_cust.vhd:96-118)."""
+    x = np.atleast_2d(np.asarray(x, dtype=np.int16))
+    c = x.shape[0]
+    k = np.asarray(coeff6x6, dtype=np.int64).reshape(6, 6)
+    if state is None:
+        state = np.zeros((c, 6, 4), dtype=np.int16)
+    state = np.asarray(state, dtype=np.int16).reshape(c, 6, 4)
+    new_state = np.empty_like(state)
+    v = x
+    for s in range(6):
+        v, new_state[:, s, :] = biquad(v, tuple(int(t) for t in k[s, :5]), state[:, s, :])
+    return v, new_state
+
+
 # --------------------------------------------------------------------------- a7
 class CommandDecoder:
     """Byte protocol of the control plane, restating

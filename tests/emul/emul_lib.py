@@ -87,6 +87,10 @@ class EmulFra:
         assert rc == 0, (rc, self.L.fra_last_cuda_error(self.h))
         return out
 
+    def load_sections(self, coeff6x6):
+        arr = (C.c_int8 * 36)(*[int(v) for v in np.asarray(coeff6x6).reshape(36)])
+        assert self.L.fra_load_sections(self.h, arr) == 0
+
     def get_state(self):
         st = np.zeros((self.c, 6, 4), np.int16)
         assert self.L.fra_get_state(self.h, st.ctypes.data, None) == 0

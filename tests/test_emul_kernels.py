@@ -51,6 +51,37 @@ def test_k1_bit_exact_with_state_and_reload(flags, name, channels, rom):
         f.close()
 
 
+@pytest.mark.parametrize("flags", [_abi.FRA_K1_FORCE_LANE, _abi.FRA_K1_FORCE_SPLIT, _abi.FRA_K1_FORCE_STAGE,
+                                   _abi.FRA_K1_FORCE_DUO])
+def test_six_independent_sections(flags, rom):
+    """fra_load_sections: every stage its own coefficients."""
+    rng = np.random.default_rng(21)
+    c, n = 5, 1024
+    f = EmulFra(c, n, flags)
+    try:
+        for trial in range(2):
+            sec = rng.integers(-128, 128, (6, 6)).astype(np.int8)
+            if trial == 1:
+                sec[:, 4] = rng.integers(-60, 61, 6)          # k1_duo's two-instruction recurrence
+                sec[:, 1] = 0                                 # and the skipped x[n-1] product
+            f.load_sections(sec)
+            f.command(bytes([0xA1]))
+            st0 = rng.integers(-32768, 32768, (c, 6, 4)).astype(np.int16)
+            f.set_state(st0)
+            x = adversarial(rng, c, n)
+            y, st = cg.window_iir_sections(x, rom, sec, st0)
+            out = f.process(x, continuous=True, want=("filtered",))
+            assert np.array_equal(out["filtered"], y) and np.array_equal(f.get_state(), st)
+        # a 12-byte upload restores the RTL's two alternating sets
+        f.command(bytes([0xF1]) + B1.tobytes())
+        x = adversarial(rng, c, n)
+        y, st = cg.window_iir(x, rom, 0xA1, g.BANK0_COEFF, B1)
+        out = f.process(x, continuous=False, want=("filtered",))
+        assert np.array_equal(out["filtered"], y)
+    finally:
+        f.close()
+
+
 def test_pipeline_flag_same_results(rom):
     """FRA_PIPELINE only changes which streams the kernels go to: the host logic around it
     (two scratch buffers, hand-over events) must leave results and state unchanged."""

@@ -331,3 +331,33 @@ def test_process_host_async_matches_sync(fra, rom):
     for x in xs:
         y, st = cg.window_iir(x.numpy()[:8], rom, 0x00, g.BANK0_COEFF, B1, st)
     assert np.array_equal(pending[0]["filtered"].numpy()[:8], y)
+
+
+@pytest.mark.parametrize("variant", ["lane", "split", "stage", "duo", "auto"])
+def test_six_independent_sections(fra, rom, variant):
+    """fra_load_sections: every stage its own coefficients, bit-exact."""
+    flags = {"lane": fra._abi.FRA_K1_FORCE_LANE, "split": fra._abi.FRA_K1_FORCE_SPLIT,
+             "stage": fra._abi.FRA_K1_FORCE_STAGE, "duo": fra._abi.FRA_K1_FORCE_DUO, "auto": 0}[variant]
+    rng = np.random.default_rng(31)
+    c, n = 45, 16384
+    with fra.FraContext(c, n, flags=flags) as ctx:
+        for trial in range(3):
+            sec = rng.integers(-128, 128, (6, 6)).astype(np.int8)
+            if trial >= 1:
+                sec[:, 4] = rng.integers(-60, 61, 6)
+            if trial == 2:
+                sec[:, 1] = 0
+            ctx.load_sections(sec)
+            ctx.set_mode(0xA1)
+            assert np.array_equal(ctx.sections(), sec)
+            st0 = rng.integers(-32768, 32768, (c, 6, 4)).astype(np.int16)
+            ctx.set_state(dev(st0))
+            x = adversarial(rng, c, n)
+            y, st = cg.window_iir_sections(x, rom, sec, st0)
+            out = ctx.process(dev(x), continuous=True, want=("filtered",))
+            assert np.array_equal(out["filtered"].cpu().numpy(), y), (variant, trial)
+            assert np.array_equal(ctx.get_state().cpu().numpy(), st)
+        ctx.load_bank1(B1)                                   # back to the RTL's two alternating sets
+        assert np.array_equal(ctx.sections(), np.stack([B1[:6], B1[6:]] * 3))
+        ctx.set_mode(0x00)
+        assert np.array_equal(ctx.sections(), np.stack([g.BANK0_COEFF[:6], g.BANK0_COEFF[6:]] * 3))
