@@ -28,6 +28,24 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 # stdout carries exactly one JSON line: NCCL's own banner / debug output goes to stderr
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """Keep the real stdout for the JSON line and point file descriptor 1 at stderr, so that
+    nothing a library prints (NCCL's version banner ignores NCCL_DEBUG_FILE on some builds)
+    can share the stream the driver parses."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 CHANNELS = 4096
 N = 16384
@@ -121,7 +139,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------ GPU arm
@@ -310,7 +328,7 @@ def run_ours(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": channels * N * 2,
                         "d2h_bytes_per_step": channels * N * 4, "steps": e2e_steps},
                 "gpu_launches": launches, "clocks": clocks}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -325,6 +343,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()
+    claim_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
