@@ -170,7 +170,7 @@ class ClockSampler:
                 for name, bit in names.items():
                     if r & bit:
                         self.reasons.add(name)
-                time.sleep(0.002)
+                time.sleep(float(os.environ.get("FRA_BENCH_SAMPLE_S", "0.002")))
             nv.nvmlShutdown()
         except Exception as e:           # noqa: BLE001
             self.err = repr(e)

@@ -322,6 +322,7 @@ int pipe_init(fra_ctx *ctx)
     if (ctx->pipe_k1) return FRA_OK;
     int lo = 0, hi = 0;                                        // hi is the numerically smaller value
     FRA_TRY(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    // window+IIR first: measured 0.2725 ms/step against 0.276 with equal priorities and 0.326 with the FFT first
     FRA_TRY(ctx, cudaStreamCreateWithPriority(&ctx->pipe_k1, cudaStreamNonBlocking, hi));
     FRA_TRY(ctx, cudaStreamCreateWithPriority(&ctx->pipe_k2, cudaStreamNonBlocking, lo));
     FRA_TRY(ctx, cudaEventCreateWithFlags(&ctx->pipe_in, cudaEventDisableTiming));

@@ -610,9 +610,14 @@ constexpr int kDuoRomBytes = kStageChunk * 4;             // the chunk's 64 wind
 constexpr int kDuoInOff = kDuoTilesBytes;                                   // raw input lines, 2 buffers
 constexpr int kDuoRomOff = kDuoInOff + 2 * kDuoLineTileBytes;               // ROM slices, 2 buffers
 constexpr int kDuoSmemBytes = kDuoRomOff + 2 * kDuoRomBytes;                // 72.5 KiB
-// requested size: padded so that at most TWO CTAs share an SM - a third adds no throughput (the
-// three stage-pair schedulers are issue-bound with two) and makes the tail wave longer
-constexpr int kDuoSmemRequest = 77 * 1024;
+// requested size: padded to 96 KiB.  (1) At most TWO CTAs share an SM - a third adds no
+// throughput (the three stage-pair schedulers are issue-bound with two) and makes the tail wave
+// longer.  (2) In FRA_PIPELINE mode the FFT kernel's CTAs (64 KiB each) run beside this kernel:
+// one CTA of this kernel and two of the FFT fit an SM (97 + 65 + 65 KiB), but TWO of this
+// kernel beside an FFT CTA do not, so its 128 CTAs cannot double up on SMs the FFT already
+// occupies - that placement halves their speed and, once entered after a host hiccup, persisted
+// from step to step (bench: 0.303 instead of 0.273 ms).
+constexpr int kDuoSmemRequest = 96 * 1024;
 
 FRA_DEV int duo_swz(int row, int piece) { return row * 128 + ((piece ^ (row & 7)) << 4); }
 
