@@ -59,6 +59,10 @@ struct fra_ctx {
     int16_t *d_state = nullptr;       // [C][6][4]
     int16_t *d_scratch = nullptr;     // [C][N] filter output when the caller does not ask for it
     float2 *d_tw1 = nullptr, *d_tw2 = nullptr, *d_twn = nullptr;
+    // 64K frames: W_65536^k and the scratch of the even/odd decomposition (k2_fft.cuh)
+    float2 *d_twc = nullptr, *d_halves = nullptr;
+    int16_t *d_split = nullptr;
+    size_t split_frames = 0;
     // staging for fra_process_host
     int16_t *d_in = nullptr;
     uint8_t *d_frames = nullptr;
@@ -187,6 +191,74 @@ int launch_k2_n(fra_ctx *ctx, const K2Args &args, bool win, int qmode, cudaStrea
     return launch_k2_inst<LOG2N, false, 2>(ctx, args, st);
 }
 
+// N = 65536: split into even / odd 32K frames, the 32K kernel on both, radix-2 join
+int launch_k2_64k(fra_ctx *ctx, const K2Args &args, bool win, int qmode, cudaStream_t st)
+{
+    // scratch is indexed by the frame's position in the context, so channel slices on different
+    // streams (fra_process_host) do not share it
+    const size_t frames = (size_t)args.batch;
+    const size_t need = std::max<size_t>((size_t)ctx->channels, (size_t)args.frame0 + frames);
+    if (ctx->split_frames < need) {
+        FRA_TRY(ctx, cudaDeviceSynchronize());                 // other slices may still be using the old scratch
+        if (ctx->d_split) FRA_TRY(ctx, cudaFree(ctx->d_split));
+        if (ctx->d_halves) FRA_TRY(ctx, cudaFree(ctx->d_halves));
+        ctx->d_split = nullptr;
+        ctx->d_halves = nullptr;
+        ctx->split_frames = 0;
+        if (cudaMalloc((void **)&ctx->d_split, need * 2 * kHalf64k * sizeof(int16_t)) != cudaSuccess ||
+            cudaMalloc((void **)&ctx->d_halves, need * 2 * kHalf64k * sizeof(float2)) != cudaSuccess)
+            return FRA_ERR_NOMEM;
+        ctx->split_frames = need;
+    }
+    int16_t *split = ctx->d_split + (size_t)args.frame0 * 2 * kHalf64k;
+    float2 *halves = ctx->d_halves + (size_t)args.frame0 * 2 * kHalf64k;
+    const size_t total8 = frames * (2 * kHalf64k / 8);
+    const int16_t *in16 = reinterpret_cast<const int16_t *>(args.in);
+    if (win) {
+        auto kfn = k2_split64k<true>;
+        FRA_LAUNCH(kfn, dim3((unsigned)((total8 + 255) / 256)), dim3(256), (size_t)0, st, in16, split,
+                   (const int *)ctx->d_rom32, total8);
+    } else {
+        auto kfn = k2_split64k<false>;
+        FRA_LAUNCH(kfn, dim3((unsigned)((total8 + 255) / 256)), dim3(256), (size_t)0, st, in16, split,
+                   (const int *)ctx->d_rom32, total8);
+    }
+    FRA_TRY(ctx, cudaGetLastError());
+    ctx->last_kernels++;
+
+    K2Args half = args;
+    half.in = reinterpret_cast<const uint32_t *>(split);
+    half.frames = nullptr;
+    half.iq = halves;
+    half.mag = nullptr;
+    half.phase = nullptr;
+    half.batch = 2 * args.batch;
+    int rc = launch_k2_inst<15, false, 0>(ctx, half, st);
+    if (rc != FRA_OK) return rc;
+
+    BinOut o;
+    o.frames = args.frames;
+    o.iq = args.iq;
+    o.mag = args.mag;
+    o.phase = args.phase;
+    o.qscale = args.qscale;
+    const size_t total = frames * kHalf64k;
+    const dim3 grid((unsigned)((total + 255) / 256));
+    if (qmode == 0) {
+        auto kfn = k2_join64k<0>;
+        FRA_LAUNCH(kfn, grid, dim3(256), (size_t)0, st, (const float2 *)halves, (const float2 *)ctx->d_twc, o, total);
+    } else if (qmode == 1) {
+        auto kfn = k2_join64k<1>;
+        FRA_LAUNCH(kfn, grid, dim3(256), (size_t)0, st, (const float2 *)halves, (const float2 *)ctx->d_twc, o, total);
+    } else {
+        auto kfn = k2_join64k<2>;
+        FRA_LAUNCH(kfn, grid, dim3(256), (size_t)0, st, (const float2 *)halves, (const float2 *)ctx->d_twc, o, total);
+    }
+    FRA_TRY(ctx, cudaGetLastError());
+    ctx->last_kernels++;
+    return FRA_OK;
+}
+
 int launch_k2(fra_ctx *ctx, const K2Args &args, bool win, int qmode, cudaStream_t st)
 {
     switch (ctx->log2n) {
@@ -196,6 +268,7 @@ int launch_k2(fra_ctx *ctx, const K2Args &args, bool win, int qmode, cudaStream_
     case 13: return launch_k2_n<13>(ctx, args, win, qmode, st);
     case 14: return launch_k2_n<14>(ctx, args, win, qmode, st);
     case 15: return launch_k2_n<15>(ctx, args, win, qmode, st);
+    case 16: return launch_k2_64k(ctx, args, win, qmode, st);
     default: return FRA_ERR_UNSUPPORTED;
     }
 }
@@ -303,6 +376,7 @@ int process_range(fra_ctx *ctx, const int16_t *d_in, int c0, int nch, int contin
         k2.phase = o.d_phase;
         k2.qscale = std::ldexp(0.5f, log2_scale);
         k2.batch = nch;
+        k2.frame0 = c0;
         k2.exp23 = 0x4B000000u;
         const bool nearest = (ctx->flags & FRA_ROUND_NEAREST) != 0;
         const int qmode = nearest ? 2 : (log2_scale <= -ctx->log2n ? 0 : 1);
@@ -397,7 +471,7 @@ int fra_create(fra_ctx **out, int device, int n_channels, int fft_size, unsigned
     int log2n = 0;
     while ((1 << log2n) < fft_size) ++log2n;
     if ((1 << log2n) != fft_size) return FRA_ERR_INVALID;
-    if (log2n < 10 || log2n > 15) return FRA_ERR_UNSUPPORTED;
+    if (log2n < 10 || log2n > 16) return FRA_ERR_UNSUPPORTED;
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return FRA_ERR_NO_DEVICE;
     if (device < 0 || device >= count) return FRA_ERR_INVALID;
@@ -424,11 +498,13 @@ int fra_create(fra_ctx **out, int device, int n_channels, int fft_size, unsigned
     if (cudaMalloc((void **)&ctx->d_state, (size_t)n_channels * 24 * sizeof(int16_t)) != cudaSuccess) return bail(FRA_ERR_NOMEM);
     if (cudaMalloc((void **)&ctx->d_tw1, 256 * sizeof(float2)) != cudaSuccess) return bail(FRA_ERR_NOMEM);
     if (cudaMalloc((void **)&ctx->d_tw2, 4096 * sizeof(float2)) != cudaSuccess) return bail(FRA_ERR_NOMEM);
-    if (cudaMalloc((void **)&ctx->d_twn, (n / 2) * sizeof(float2)) != cudaSuccess) return bail(FRA_ERR_NOMEM);
+    // the in-kernel FFT is the frame itself up to 32K, and each half of a 64K frame
+    const size_t n_kernel = std::min<size_t>(n, (size_t)kHalf64k);
+    if (cudaMalloc((void **)&ctx->d_twn, (n_kernel / 2) * sizeof(float2)) != cudaSuccess) return bail(FRA_ERR_NOMEM);
 
     std::vector<int> rom32(kWindowLen);
     for (int i = 0; i < kWindowLen; ++i) rom32[i] = kHannRom[i];
-    std::vector<float2> tw1(256), tw2(4096), twn(n / 2);
+    std::vector<float2> tw1(256), tw2(4096), twn(n_kernel / 2);
     const double two_pi = 6.283185307179586476925286766559;
     for (int r = 0; r < 16; ++r)
         for (int k = 0; k < 16; ++k) {
@@ -440,9 +516,19 @@ int fra_create(fra_ctx **out, int device, int n_channels, int fft_size, unsigned
             double a = -two_pi * (double)(r * k) / 4096.0;
             tw2[r * 256 + k] = make_float2((float)std::cos(a), (float)std::sin(a));
         }
-    for (size_t e = 0; e < n / 2; ++e) {
-        double a = -two_pi * (double)e / (double)n;
+    for (size_t e = 0; e < n_kernel / 2; ++e) {
+        double a = -two_pi * (double)e / (double)n_kernel;
         twn[e] = make_float2((float)std::cos(a), (float)std::sin(a));
+    }
+    if (n > n_kernel) {
+        std::vector<float2> twc(kHalf64k);
+        for (int k = 0; k < kHalf64k; ++k) {
+            double a = -two_pi * (double)k / (double)n;
+            twc[k] = make_float2((float)std::cos(a), (float)std::sin(a));
+        }
+        if (cudaMalloc((void **)&ctx->d_twc, twc.size() * sizeof(float2)) != cudaSuccess) return bail(FRA_ERR_NOMEM);
+        if (cudaMemcpy(ctx->d_twc, twc.data(), twc.size() * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess)
+            return bail(FRA_ERR_CUDA);
     }
     if (cudaMemcpy(ctx->d_rom32, rom32.data(), rom32.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(ctx->d_tw1, tw1.data(), tw1.size() * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess ||
@@ -467,7 +553,7 @@ int fra_destroy(fra_ctx *ctx)
         if (ps) { cudaStreamSynchronize(ps); cudaStreamDestroy(ps); }
     for (cudaEvent_t pe : {ctx->pipe_in, ctx->pipe_k1_done[0], ctx->pipe_k1_done[1], ctx->pipe_k2_done[0], ctx->pipe_k2_done[1]})
         if (pe) cudaEventDestroy(pe);
-    void *bufs[] = {ctx->d_rom32, ctx->d_state, ctx->d_scratch, ctx->d_tw1, ctx->d_tw2, ctx->d_twn, ctx->d_in,
+    void *bufs[] = {ctx->d_rom32, ctx->d_state, ctx->d_scratch, ctx->d_tw1, ctx->d_tw2, ctx->d_twn, ctx->d_in, ctx->d_twc, ctx->d_halves, ctx->d_split,
                     ctx->d_frames, ctx->d_filtered_out, ctx->d_iq, ctx->d_mag, ctx->d_phase, ctx->d_entry,
                     ctx->d_exit, ctx->d_counts, ctx->d_ends, ctx->d_aggr, ctx->d_mats};
     for (void *p : bufs)
@@ -977,6 +1063,7 @@ int fra_fft_only(fra_ctx *ctx, const int16_t *d_in, int batch, float *d_iq, void
     k2.phase = nullptr;
     k2.qscale = std::ldexp(0.5f, -ctx->log2n);
     k2.batch = batch;
+    k2.frame0 = 0;
     k2.exp23 = 0x4B000000u;
     ctx->last_kernels = 0;
     return launch_k2(ctx, k2, /*win=*/false, /*qmode=*/0, st);

@@ -35,6 +35,7 @@ struct K2Args {
     float qscale;           // 0.5 * 2^log2_scale (the untangle leaves 2 X[k])
     int batch;
     unsigned exp23;         // 0x4B000000 as data (keeps PRMT's selector an immediate)
+    int frame0;             // host side only: index of the first frame within the context (scratch offset of the 64K path)
 };
 
 template <int LOG2N>
@@ -393,6 +394,54 @@ __global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS, (LOG2N == 15) ? 1 : 3
         const int k = (tid & 1) ? (P::L / 2) : 0;
         if (frame0 + fr < a.batch) item(fr, k, __ldg(a.twn + k));
     }
+}
+
+// ------------------------------------------------------------------ N = 65536
+// A 64K frame is 32768 complex points = 256 KiB of fp32, more than an SM's shared memory, so it
+// is done as one decimation-in-time step around the 32K kernel:
+//   k2_split64k    even / odd samples of every frame -> two 32K frames (window applied here in
+//                  bypass mode: the ROM index is the sample's index in the 64K frame)
+//   k2_fft<15,...> on 2 x batch frames, fp32 bins to scratch
+//   k2_join64k     X[k] = E[k] + W_65536^k O[k],  X[k + 32768] = E[k] - W_65536^k O[k],
+//                  then the same quantise / pack / mag / phase as the single-kernel sizes
+// 28 B of HBM traffic per sample instead of 6: the price of not fitting on chip.
+constexpr int kHalf64k = 32768;
+
+template <bool WIN>
+__global__ void __launch_bounds__(256) k2_split64k(const int16_t *in, int16_t *out, const int *rom32, size_t total8)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // one thread = 8 consecutive samples
+    if (i >= total8) return;
+    const size_t e = i * 8;
+    const size_t frame = e / (2 * kHalf64k);
+    const int n0 = (int)(e % (2 * kHalf64k));
+    const uint4 x = ldg128(in + e);
+    int v[8] = {lo16(x.x), hi16(x.x), lo16(x.y), hi16(x.y), lo16(x.z), hi16(x.z), lo16(x.w), hi16(x.w)};
+    if (WIN) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = window_int(v[j], __ldg(rom32 + ((n0 + j) & (kWindowLen - 1))));
+    }
+    uint2 ev, od;
+    ev.x = pack16((unsigned)v[0], (unsigned)v[2]); ev.y = pack16((unsigned)v[4], (unsigned)v[6]);
+    od.x = pack16((unsigned)v[1], (unsigned)v[3]); od.y = pack16((unsigned)v[5], (unsigned)v[7]);
+    int16_t *even = out + (2 * frame) * kHalf64k + n0 / 2;
+    *reinterpret_cast<uint2 *>(even) = ev;
+    *reinterpret_cast<uint2 *>(even + kHalf64k) = od;
+}
+
+template <int QMODE>
+__global__ void __launch_bounds__(256) k2_join64k(const float2 *halves, const float2 *twc, BinOut out, size_t total)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // one thread = bins k and k + 32768 of a frame
+    if (i >= total) return;
+    const size_t frame = i / kHalf64k;
+    const int k = (int)(i % kHalf64k);
+    const float2 e = halves[(2 * frame) * kHalf64k + k];
+    const float2 o = cmul(halves[(2 * frame + 1) * kHalf64k + k], __ldg(twc + k));
+    const size_t base = frame * (2 * (size_t)kHalf64k) + k;
+    // emit_pair takes 2 X (the untangle's convention) and halves it
+    emit_pair<QMODE>(out, base, 0, 0, 0, false, make_float2(2.0f * (e.x + o.x), 2.0f * (e.y + o.y)));
+    emit_pair<QMODE>(out, base, 0, kHalf64k, 0, false, make_float2(2.0f * (e.x - o.x), 2.0f * (e.y - o.y)));
 }
 
 }  // namespace fra

@@ -39,7 +39,7 @@ typedef enum fra_status {
     FRA_ERR_NO_DEVICE = -2,    /* no CUDA device / driver */
     FRA_ERR_CUDA = -3,         /* a CUDA call or kernel failed; see fra_last_cuda_error */
     FRA_ERR_NOMEM = -4,
-    FRA_ERR_UNSUPPORTED = -5,  /* e.g. fft_size not in 1024..32768 */
+    FRA_ERR_UNSUPPORTED = -5,  /* e.g. fft_size not in 1024..65536 */
     FRA_ERR_BUSY = -6          /* byte stream ended inside a 0xF1 upload (informational) */
 } fra_status;
 
@@ -74,7 +74,7 @@ typedef enum fra_status {
 
 typedef struct fra_ctx fra_ctx;      /* opaque: ROM, two coefficient banks, IIR state, twiddles, one stream */
 
-/* Lifetime.  n_channels independent channels, fft_size in {1024,...,32768}
+/* Lifetime.  n_channels independent channels, fft_size in {1024,...,65536}
  * (the reference is fixed at 16384: IP/xfft_0/xfft_0.xci:12, IMP/dsp_system_top.vhd:438-449).
  * After create the control state is the RTL's reset state: mode 0xB1, bank 1 all
  * zero, IIR history zero, window address 0. */

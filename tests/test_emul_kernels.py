@@ -129,7 +129,7 @@ def test_k1_random_coefficients_and_user_state(rom):
                 f.close()
 
 
-@pytest.mark.parametrize("n", [1024, 2048, 4096, 8192, 16384, 32768])
+@pytest.mark.parametrize("n", [1024, 2048, 4096, 8192, 16384, 32768, 65536])
 def test_k2_fft_all_sizes_and_framing(n, rom):
     rng = np.random.default_rng(n)
     b = max(1, 16384 // n) + 1                      # more than one CTA, last CTA partly empty

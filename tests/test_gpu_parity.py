@@ -100,7 +100,7 @@ def test_k1_random_int8_coefficients_fuzz(fra, rom, seed):
             assert np.array_equal(ctx.get_state().cpu().numpy(), st)
 
 
-@pytest.mark.parametrize("n", [1024, 2048, 4096, 8192, 16384, 32768])
+@pytest.mark.parametrize("n", [1024, 2048, 4096, 8192, 16384, 32768, 65536])
 def test_fft_sizes_tolerance_and_framing(fra, rom, n):
     rng = np.random.default_rng(n)
     b = 3 * max(1, 16384 // n) + 1
@@ -361,3 +361,25 @@ def test_six_independent_sections(fra, rom, variant):
         assert np.array_equal(ctx.sections(), np.stack([B1[:6], B1[6:]] * 3))
         ctx.set_mode(0x00)
         assert np.array_equal(ctx.sections(), np.stack([g.BANK0_COEFF[:6], g.BANK0_COEFF[6:]] * 3))
+
+
+def test_64k_frames_full_chain(fra, rom):
+    """N = 65536 (BASELINE config 5's upper end): window + IIR12 bit-exact, FFT by the
+    split / 2 x 32K / join path within tolerance, host path identical."""
+    rng = np.random.default_rng(64)
+    c, n = 5, 65536
+    x = adversarial(rng, c, n)
+    with fra.FraContext(c, n) as ctx:
+        ctx.command(0x00)
+        out = {k: v.cpu().numpy() for k, v in ctx.process(dev(x), want=("filtered", "frames", "iq", "mag")).items()}
+        y, st = cg.window_iir(x, rom, 0x00, g.BANK0_COEFF, B1)
+        assert np.array_equal(out["filtered"], y)
+        assert np.array_equal(ctx.get_state().cpu().numpy(), st)
+        ref = np.fft.fft(y.astype(np.float64), axis=-1)
+        got = out["iq"][..., 0] + 1j * out["iq"][..., 1]
+        assert rel_l2(got, ref) < FFT_TOL
+        assert np.array_equal(cg.quantize_pack(got.astype(np.complex128), -16, 0), out["frames"])
+        re, im, mag = g.decode_frame(out["frames"])
+        assert np.array_equal(mag.view(np.uint32), out["mag"].view(np.uint32))
+        host = ctx.process_host(torch.from_numpy(x).pin_memory(), want=("frames",))
+        assert np.array_equal(host["frames"].numpy(), out["frames"])

@@ -23,7 +23,7 @@ with FraContext(1, 16384) as ctx:
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         print(f"stream 2^24 samples exact={int(exact)}: {dt * 1e3:.2f} ms  {n / dt / 1e9:.3f} Gsamples/s  stats={st}")
-for log2n in range(10, 16):
+for log2n in range(10, 17):
     N = 1 << log2n
     batch = (1 << 26) // N
     with FraContext(batch, N) as ctx:
@@ -40,4 +40,3 @@ for log2n in range(10, 16):
         ms = e0.elapsed_time(e1) / 5
         print(f"fft_only N={N:6d} batch={batch:6d}: {ms:.4f} ms  {batch * N / ms / 1e6:.1f} Gsamples/s (int16 in, complex64 out: "
               f"{batch * N * 10 / ms / 1e6:.0f} GB/s)")
-print("64K: not supported (needs 256 KiB of shared memory: 2-CTA cluster + DSMEM, see DESIGN.md)")
