@@ -82,7 +82,7 @@ def test_argument_validation_needs_no_device(built_lib):
     h = ctypes.c_void_p()
     assert L.fra_create(ctypes.byref(h), 0, 0, 16384, 0) == -1        # no channels
     assert L.fra_create(ctypes.byref(h), 0, 4, 12345, 0) == -1        # not a power of two
-    assert L.fra_create(ctypes.byref(h), 0, 4, 65536, 0) == -5        # outside 1K..32K
+    assert L.fra_create(ctypes.byref(h), 0, 4, 131072, 0) == -5       # outside 1K..64K
     assert L.fra_destroy(None) == -1
     assert L.fra_process(None, None, 0, 0, None, None) == -1
 
