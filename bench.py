@@ -99,6 +99,19 @@ def cpu_float_rate(cores, channels_per_proc, reps):
     return samples / dt / 1e9, samples, dt
 
 
+def profiled_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` summary
+    (profiles/r01_<kernel>_4096ch.txt, the same 4096-channel launch), or None."""
+    path = os.path.join(ROOT, "profiles", f"r01_{kernel}_4096ch.txt")
+    try:
+        for ln in open(path):
+            if ln.startswith("traffic = dram read + write per launch"):
+                return {"bytes": float(ln.split()[8]) * 1e6, "source": os.path.relpath(path, ROOT)}
+    except (OSError, ValueError, IndexError):
+        pass
+    return None
+
+
 def cpu_int_rate():
     """Context: the bit-exact C golden model (scalar, one core)."""
     import numpy as np
@@ -242,11 +255,13 @@ def run_ours(args):
     launches = 0
     barrier()
     e0.record()
+    t_host = time.perf_counter()
     for i in range(args.steps):
         step(i)
         launches += ctx.last_kernel_count
     ctx.join()                                             # the current stream waits for both internal streams
     e1.record()
+    host_enqueue_ms = 1e3 * (time.perf_counter() - t_host) / args.steps      # host time to enqueue one step
     barrier()
     elapsed_ms = e0.elapsed_time(e1)
     # per-kernel durations: events recorded inside the library around each kernel, in one more
@@ -304,9 +319,11 @@ def run_ours(args):
                 kernels[name] = {"ms": ms, "achieved_gbs": ach, "frac": ach / peak,
                                  "alg_bytes_per_sample": B_ALG[name]}
         dom = "window_iir" if k1 >= k2 else "fft_pack"
+        traffic = profiled_traffic("k1_duo" if dom == "window_iir" else "k2_fft")
         roofline = {"bound": "hbm", "kernel": ("k1_duo<true,true,true>" if dom == "window_iir" else "k2_fft<14,false,0,0>"),
                     "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                    "frac": kernels[dom]["frac"], "traffic": traffic["bytes"] if traffic else None,
+                    "traffic_source": traffic["source"] if traffic else None, "peak_source": peak_src,
                     "kernels": kernels, "sequential_ms_per_step": k1 + k2,
                     "chain": {"achieved": value / world * B_ALG["chain"], "frac": value / world * B_ALG["chain"] / peak,
                               "alg_bytes_per_sample": B_ALG["chain"]},
@@ -327,7 +344,7 @@ def run_ours(args):
                                  "int_golden_1core": cpu_int_rate()},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": channels * N * 2,
                         "d2h_bytes_per_step": channels * N * 4, "steps": e2e_steps},
-                "gpu_launches": launches, "clocks": clocks}
+                "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": clocks}
         emit(line)
     if world > 1:
         dist.barrier()
