@@ -490,8 +490,7 @@ int fra_create(fra_ctx **out, int device, int n_channels, int fft_size, unsigned
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(FRA_ERR_NO_DEVICE);
     ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(FRA_ERR_CUDA);
-    for (auto &s : ctx->copy_streams)
-        if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return bail(FRA_ERR_CUDA);
+    // the three copy streams are created by the first host-buffer call
 
     const size_t n = (size_t)fft_size;
     if (cudaMalloc((void **)&ctx->d_rom32, kWindowLen * sizeof(int)) != cudaSuccess) return bail(FRA_ERR_NOMEM);
@@ -785,6 +784,8 @@ int fra_process_host_async(fra_ctx *ctx, const int16_t *h_in, int continuous, in
 
     // pending control-plane work (a reset's memset) is ordered on ctx->stream
     FRA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    for (auto &cs : ctx->copy_streams)
+        if (!cs) FRA_TRY(ctx, cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
     ctx->last_kernels = 0;
     // channel slices round-robin over three streams: H2D(i+1) and D2H(i-1) overlap compute(i)
     const int n_slices = (int)std::min<size_t>(C, C * n >= ((size_t)1 << 24) ? 8 : 1);

@@ -37,7 +37,7 @@ if a.pipeline or a.time:
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = max(a.steps, 20)
     import time
-    if a.pipeline:
+    if a.pipeline and not os.environ.get("FRA_NO_PROFILE"):
         ctx.profile(True)
     e0.record()
     for i in range(reps):
@@ -48,7 +48,7 @@ if a.pipeline or a.time:
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    if a.pipeline:
+    if a.pipeline and not os.environ.get("FRA_NO_PROFILE"):
         t = ctx.profile_last()
         print(f"  last step's kernel spans while overlapped: K1 {t[0]:.4f} ms  K2 {t[1]:.4f} ms")
     print(f"channels={a.channels} n={a.n} pipeline={int(a.pipeline)} k1={a.k1}: {ms:.4f} ms/step  "
