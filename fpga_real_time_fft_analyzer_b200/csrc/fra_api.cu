@@ -30,7 +30,12 @@ const int16_t kHannRom[kWindowLen] = {
 const int8_t kBank0[12] = {-14, 0, 14, 107, 21, 127, -15, 0, 15, 107, -21, 127};
 
 constexpr int kStreamMaxDeadband = 32;            // LSB; larger boundary differences mean the scan is invalid
-constexpr int kLaneMinChannels = 28672;          // measured crossover: below it k1_duo (0.034 us/channel at two CTAs per SM) beats k1_lane (flat 1.0 ms)
+// k1_lane wins only in a window of channel counts: below it k1_duo is faster outright (k1_lane is flat at
+// 1.0 ms up to ~19k channels), above it k1_duo's asymptote is higher (561 vs 535 Gsamples/s at 65536 channels);
+// in between k1_duo's wave quantisation (296 CTAs of 32 channels per wave) costs more than the difference
+// (32768 channels: 1.09 vs 1.03 ms, 49152: 1.63 vs 1.53 ms)
+constexpr int kLaneMinChannels = 28672;
+constexpr int kLaneMaxChannels = 57344;
 
 }  // namespace
 
@@ -302,9 +307,9 @@ int process_range(fra_ctx *ctx, const int16_t *d_in, int c0, int nch, int contin
         k1.continuous = continuous;
         k1.speculate = (ctx->flags & FRA_K1_SPECULATE) ? 1 : 0;
         if (ctx->profiling) FRA_TRY(ctx, cudaEventRecord(ctx->ev[0], st));
-        // k1_lane needs ~19k channels to fill 592 schedulers; below that the stage-pair-per-warp
-        // pipeline k1_duo; k1_stage and the stage-per-lane systolic k1_split only on request
-        int variant = (nch < kLaneMinChannels) ? 3 : 0;          // 0 lane, 1 split, 2 stage, 3 duo
+        // k1_duo (stage pairs per warp) by default, k1_lane (a lane per channel) in the window of channel
+        // counts where it wins; k1_stage and the stage-per-lane systolic k1_split only on request
+        int variant = (nch >= kLaneMinChannels && nch < kLaneMaxChannels) ? 0 : 3;     // 0 lane, 1 split, 2 stage, 3 duo
         if (ctx->flags & FRA_K1_FORCE_LANE) variant = 0;
         if (ctx->flags & FRA_K1_FORCE_SPLIT) variant = 1;
         if (ctx->flags & FRA_K1_FORCE_STAGE) variant = 2;
