@@ -597,7 +597,7 @@ __global__ void __launch_bounds__(kStageWarps * 32, 2) k1_stage(K1Args a)
 // per SM beyond that.
 constexpr int kDuoPairs = kStages / 2;
 constexpr int kDuoWarps = 2 + kDuoPairs;                // loader, three stage pairs, writer
-constexpr int kDuoBoundaries = kDuoPairs + 1;           // loader -> pair 0 -> pair 1 -> pair 2 -> loader
+constexpr int kDuoBoundaries = kDuoPairs + 1;           // loader -> pair 0 -> pair 1 -> pair 2 -> writer
 constexpr int kDuoTilesBytes = kDuoBoundaries * 2 * kStageTileFloats * (int)sizeof(float);    // 64 KiB
 // Global memory is touched in whole 128-byte lines only: a chunk of one channel IS one line
 // (64 int16), so eight lanes move a channel's line and one warp instruction covers four
@@ -621,8 +621,8 @@ constexpr int kDuoSmemRequest = 96 * 1024;
 FRA_DEV int duo_swz(int row, int piece) { return row * 128 + ((piece ^ (row & 7)) << 4); }
 
 // Every stage warp runs the SAME branch-free straight-line chunk body: the last pair also
-// leaves its output as a float tile, and the loader warp (which has the spare issue slots)
-// packs it to int16.  Two earlier versions are why: per-role instantiations overflowed the
+// leaves its output as a float tile, and the writer warp (on the scheduler the pair warps do
+// not use) packs it to int16.  Two earlier versions are why: per-role instantiations overflowed the
 // 32 KB instruction-cache level ("no_instruction" 2.2 of 4.3 stall slots), and a run-time
 // `last` branch per group is a basic-block boundary that drains both dependency chains four
 // times per chunk (21.4 instead of 17.9 cycles per sample).
