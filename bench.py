@@ -83,7 +83,7 @@ def _cpu_worker(args):
 
 
 CPU_REPS = 40
-MIN_WARMUP = 50
+MIN_WARMUP = 10         # untimed steps actually run before the timed loop (the flag's value is what the line reports)
 
 
 def cpu_float_rate(cores, channels_per_proc, reps):
@@ -251,10 +251,6 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
         time.sleep(0.05)                                   # NVML initialised before the GPU gets busy
-    # The pipelined loop settles into one of two steady states during its first steps and keeps it:
-    # 0.268 ms per step, or 0.300 (no overlap gained).  After 3 warm-up steps the timed loop drew the
-    # slow one in 4 runs of 6, after 40 in 0 of 6 (same box, interleaved) - so the warm-up is at
-    # least MIN_WARMUP steps (13 ms); the flag's value is still what the JSON line reports.
     warmup_run = max(args.warmup, MIN_WARMUP)
     for i in range(warmup_run):
         step(i)

@@ -83,6 +83,11 @@ struct fra_ctx {
     cudaStream_t pipe_k1 = nullptr, pipe_k2 = nullptr;
     cudaEvent_t pipe_in = nullptr, pipe_k1_done[2] = {nullptr, nullptr}, pipe_k2_done[2] = {nullptr, nullptr};
     unsigned long long pipe_calls = 0;
+    cudaEvent_t pipe_go = nullptr;    // recorded on pipe_k1 right before a window+IIR launch
+    bool fft_pending = false;         // the FFT of the previous call, launched behind the next call's window+IIR
+    K2Args fft_args;
+    bool fft_win = false;
+    int fft_qmode = 0, fft_buf = 0;
     // fra_process_host_async: completion events per call slot (two calls in flight) and copy stream
     cudaEvent_t host_done[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
     unsigned long long host_calls = 0;
@@ -280,12 +285,22 @@ int launch_k2(fra_ctx *ctx, const K2Args &args, bool win, int qmode, cudaStream_
 
 // One step over channels [c0, c0 + nch): pointers in `o` and d_in are already
 // offset to channel c0.
-// st: stream of the window+IIR kernel; st2 / k1_done: when given, the FFT kernel runs on st2
-// after k1_done (recorded on st behind the window+IIR kernel); scratch: filter output buffer
-// for the whole context when the caller does not ask for it
+// scratch: filter output buffer for the whole context when the caller does not ask for it
+int launch_fft(fra_ctx *ctx, const K2Args &k2, bool win, int qmode, cudaStream_t st)
+{
+    if (ctx->profiling) FRA_TRY(ctx, cudaEventRecord(ctx->ev[2], st));
+    int rc = launch_k2(ctx, k2, win, qmode, st);
+    if (rc != FRA_OK) return rc;
+    if (ctx->profiling) {
+        FRA_TRY(ctx, cudaEventRecord(ctx->ev[3], st));
+        ctx->ev_k2 = true;
+    }
+    return FRA_OK;
+}
+
+// defer_fft (FRA_PIPELINE): the FFT launch is not enqueued but left in ctx->fft_args for the caller
 int process_range(fra_ctx *ctx, const int16_t *d_in, int c0, int nch, int continuous, int log2_scale,
-                  const fra_outputs &o, cudaStream_t st, cudaStream_t st2 = nullptr, cudaEvent_t k1_done = nullptr,
-                  int16_t *scratch = nullptr)
+                  const fra_outputs &o, cudaStream_t st, bool defer_fft = false, int16_t *scratch = nullptr)
 {
     if (!scratch) scratch = ctx->d_scratch;
     const int n = ctx->n;
@@ -306,6 +321,9 @@ int process_range(fra_ctx *ctx, const int16_t *d_in, int c0, int nch, int contin
         k1.n = n;
         k1.continuous = continuous;
         k1.speculate = (ctx->flags & FRA_K1_SPECULATE) ? 1 : 0;
+#ifdef FRA_TIMELINE
+        k1.tl_step = (int)ctx->pipe_calls;
+#endif
         if (ctx->profiling) FRA_TRY(ctx, cudaEventRecord(ctx->ev[0], st));
         // k1_duo (stage pairs per warp) by default, k1_lane (a lane per channel) in the window of channel
         // counts where it wins; k1_stage and the stage-per-lane systolic k1_split only on request
@@ -363,11 +381,6 @@ int process_range(fra_ctx *ctx, const int16_t *d_in, int c0, int nch, int contin
         ctx->last_kernels++;
     }
 
-    if (k1_done) {
-        FRA_TRY(ctx, cudaEventRecord(k1_done, st));
-        FRA_TRY(ctx, cudaStreamWaitEvent(st2, k1_done, 0));
-        st = st2;
-    }
     if (want_fft) {
         K2Args k2;
         k2.in = reinterpret_cast<const uint32_t *>(fft_in);
@@ -382,16 +395,20 @@ int process_range(fra_ctx *ctx, const int16_t *d_in, int c0, int nch, int contin
         k2.qscale = std::ldexp(0.5f, log2_scale);
         k2.batch = nch;
         k2.frame0 = c0;
+#ifdef FRA_TIMELINE
+        k2.tl_step = (int)ctx->pipe_calls;
+#endif
         k2.exp23 = 0x4B000000u;
         const bool nearest = (ctx->flags & FRA_ROUND_NEAREST) != 0;
         const int qmode = nearest ? 2 : (log2_scale <= -ctx->log2n ? 0 : 1);
-        if (ctx->profiling) FRA_TRY(ctx, cudaEventRecord(ctx->ev[2], st));
-        int rc = launch_k2(ctx, k2, /*win=*/!iir, qmode, st);
-        if (rc != FRA_OK) return rc;
-        if (ctx->profiling) {
-            FRA_TRY(ctx, cudaEventRecord(ctx->ev[3], st));
-            ctx->ev_k2 = true;
+        if (defer_fft) {
+            ctx->fft_args = k2;
+            ctx->fft_win = !iir;
+            ctx->fft_qmode = qmode;
+            ctx->fft_pending = true;
+            return FRA_OK;
         }
+        return launch_fft(ctx, k2, /*win=*/!iir, qmode, st);
     }
     return FRA_OK;
 }
@@ -405,6 +422,7 @@ int pipe_init(fra_ctx *ctx)
     FRA_TRY(ctx, cudaStreamCreateWithPriority(&ctx->pipe_k1, cudaStreamNonBlocking, hi));
     FRA_TRY(ctx, cudaStreamCreateWithPriority(&ctx->pipe_k2, cudaStreamNonBlocking, lo));
     FRA_TRY(ctx, cudaEventCreateWithFlags(&ctx->pipe_in, cudaEventDisableTiming));
+    FRA_TRY(ctx, cudaEventCreateWithFlags(&ctx->pipe_go, cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i) {
         FRA_TRY(ctx, cudaEventCreateWithFlags(&ctx->pipe_k1_done[i], cudaEventDisableTiming));
         FRA_TRY(ctx, cudaEventCreateWithFlags(&ctx->pipe_k2_done[i], cudaEventDisableTiming));
@@ -412,10 +430,23 @@ int pipe_init(fra_ctx *ctx)
     return FRA_OK;
 }
 
+// The FFT of the last call, if still held back: behind that call's window+IIR kernel.
+int pipe_flush_fft(fra_ctx *ctx)
+{
+    if (!ctx->fft_pending) return FRA_OK;
+    ctx->fft_pending = false;
+    FRA_TRY(ctx, cudaStreamWaitEvent(ctx->pipe_k2, ctx->pipe_k1_done[ctx->fft_buf], 0));
+    int rc = launch_fft(ctx, ctx->fft_args, ctx->fft_win, ctx->fft_qmode, ctx->pipe_k2);
+    if (rc != FRA_OK) return rc;
+    FRA_TRY(ctx, cudaEventRecord(ctx->pipe_k2_done[ctx->fft_buf], ctx->pipe_k2));
+    return FRA_OK;
+}
+
 // host waits for the two pipeline streams (before anything that touches state or scratch
 // from another stream)
 cudaError_t pipe_host_join(fra_ctx *ctx)
 {
+    if (pipe_flush_fft(ctx) != FRA_OK) return cudaErrorUnknown;
     cudaError_t e = ctx->pipe_k1 ? cudaStreamSynchronize(ctx->pipe_k1) : cudaSuccess;
     if (e == cudaSuccess && ctx->pipe_k2) e = cudaStreamSynchronize(ctx->pipe_k2);
     return e;
@@ -555,7 +586,7 @@ int fra_destroy(fra_ctx *ctx)
             if (e) cudaEventDestroy(e);
     for (cudaStream_t ps : {ctx->pipe_k1, ctx->pipe_k2})
         if (ps) { cudaStreamSynchronize(ps); cudaStreamDestroy(ps); }
-    for (cudaEvent_t pe : {ctx->pipe_in, ctx->pipe_k1_done[0], ctx->pipe_k1_done[1], ctx->pipe_k2_done[0], ctx->pipe_k2_done[1]})
+    for (cudaEvent_t pe : {ctx->pipe_in, ctx->pipe_go, ctx->pipe_k1_done[0], ctx->pipe_k1_done[1], ctx->pipe_k2_done[0], ctx->pipe_k2_done[1]})
         if (pe) cudaEventDestroy(pe);
     void *bufs[] = {ctx->d_rom32, ctx->d_state, ctx->d_scratch, ctx->d_tw1, ctx->d_tw2, ctx->d_twn, ctx->d_in, ctx->d_twc, ctx->d_halves, ctx->d_split,
                     ctx->d_frames, ctx->d_filtered_out, ctx->d_iq, ctx->d_mag, ctx->d_phase, ctx->d_entry,
@@ -709,8 +740,15 @@ int fra_process(fra_ctx *ctx, const int16_t *d_in, int continuous, int log2_scal
     if (!pipe) return process_range(ctx, d_in, 0, ctx->channels, continuous, log2_scale, *out, st);
 
     // ---- FRA_PIPELINE: K1(i) on pipe_k1 (high priority: its few long-lived CTAs are placed
-    // first), K2(i) on pipe_k2 behind it, so K2(i) and K1(i+1) share the SMs.  Two filter
-    // scratch buffers alternate; K1(i) waits for K2(i-2), the last reader of its buffer.
+    // first), K2(i-1) on pipe_k2 beside it.  Two filter scratch buffers alternate; K1(i) waits
+    // for K2(i-2), the last reader of its buffer.
+    //
+    // The FFT of call i-1 is enqueued HERE, behind an event recorded right before K1(i)'s
+    // launch, not in call i-1.  Released by K1(i-1)'s completion alone it started ~13 us before
+    // K1(i) - whose stream still had that completion's event record and two event waits to work
+    // through - and filled every SM three CTAs deep; K1(i)'s CTAs then trickled in as FFT CTAs
+    // retired (tools/timeline_probe.py: K1 span 316 us instead of 264, step 0.300 instead of
+    // 0.268 ms; which of the two a run got depended on its first steps).
     int rc = pipe_init(ctx);
     if (rc != FRA_OK) return rc;
     const int buf = (int)(ctx->pipe_calls & 1);
@@ -718,12 +756,29 @@ int fra_process(fra_ctx *ctx, const int16_t *d_in, int continuous, int log2_scal
     FRA_TRY(ctx, cudaStreamWaitEvent(ctx->pipe_k1, ctx->pipe_in, 0));
     if (ctx->pipe_calls >= 2) FRA_TRY(ctx, cudaStreamWaitEvent(ctx->pipe_k1, ctx->pipe_k2_done[buf], 0));
     // a caller-owned filter output is rewritten every call: the previous FFT must have read it
-    if (out->d_filtered && ctx->pipe_calls >= 1)
+    if (out->d_filtered && ctx->pipe_calls >= 1) {
+        rc = pipe_flush_fft(ctx);
+        if (rc != FRA_OK) return rc;
         FRA_TRY(ctx, cudaStreamWaitEvent(ctx->pipe_k1, ctx->pipe_k2_done[buf ^ 1], 0));
-    rc = process_range(ctx, d_in, 0, ctx->channels, continuous, log2_scale, *out, ctx->pipe_k1, ctx->pipe_k2,
-                       ctx->pipe_k1_done[buf], ctx->d_scratch ? ctx->d_scratch + (size_t)buf * frame_elems : nullptr);
+    }
+    FRA_TRY(ctx, cudaEventRecord(ctx->pipe_go, ctx->pipe_k1));
+    const bool had_pending = ctx->fft_pending;
+    const K2Args prev_args = ctx->fft_args;
+    const bool prev_win = ctx->fft_win;
+    const int prev_qmode = ctx->fft_qmode, prev_buf = ctx->fft_buf;
+    ctx->fft_pending = false;
+    rc = process_range(ctx, d_in, 0, ctx->channels, continuous, log2_scale, *out, ctx->pipe_k1, /*defer_fft=*/true,
+                       ctx->d_scratch ? ctx->d_scratch + (size_t)buf * frame_elems : nullptr);
     if (rc != FRA_OK) return rc;
-    FRA_TRY(ctx, cudaEventRecord(ctx->pipe_k2_done[buf], ctx->pipe_k2));
+    FRA_TRY(ctx, cudaEventRecord(ctx->pipe_k1_done[buf], ctx->pipe_k1));
+    ctx->fft_buf = buf;
+    if (had_pending) {
+        FRA_TRY(ctx, cudaStreamWaitEvent(ctx->pipe_k2, ctx->pipe_go, 0));
+        FRA_TRY(ctx, cudaStreamWaitEvent(ctx->pipe_k2, ctx->pipe_k1_done[prev_buf], 0));
+        rc = launch_fft(ctx, prev_args, prev_win, prev_qmode, ctx->pipe_k2);
+        if (rc != FRA_OK) return rc;
+        FRA_TRY(ctx, cudaEventRecord(ctx->pipe_k2_done[prev_buf], ctx->pipe_k2));
+    }
     ctx->pipe_calls++;
     return FRA_OK;
 }
@@ -734,8 +789,12 @@ int fra_join(fra_ctx *ctx, void *cuda_stream)
     if (!(ctx->flags & FRA_PIPELINE) || ctx->pipe_calls == 0) return FRA_OK;
     FRA_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
+    int rc = pipe_flush_fft(ctx);
+    if (rc != FRA_OK) return rc;
     // pipe_k2 is in order, so its newest event covers every earlier call; the window+IIR kernel of
-    // the last call finished before that call's FFT started
+    // the last call finished before that call's FFT started.  (A call without FFT outputs leaves
+    // only its window+IIR event.)
+    FRA_TRY(ctx, cudaStreamWaitEvent(st, ctx->pipe_k1_done[(ctx->pipe_calls - 1) & 1], 0));
     FRA_TRY(ctx, cudaStreamWaitEvent(st, ctx->pipe_k2_done[(ctx->pipe_calls - 1) & 1], 0));
     return FRA_OK;
 }
@@ -1070,6 +1129,9 @@ int fra_fft_only(fra_ctx *ctx, const int16_t *d_in, int batch, float *d_iq, void
     k2.qscale = std::ldexp(0.5f, -ctx->log2n);
     k2.batch = batch;
     k2.frame0 = 0;
+#ifdef FRA_TIMELINE
+    k2.tl_step = -1;
+#endif
     k2.exp23 = 0x4B000000u;
     ctx->last_kernels = 0;
     return launch_k2(ctx, k2, /*win=*/false, /*qmode=*/0, st);
@@ -1114,6 +1176,20 @@ int fra_sync(fra_ctx *ctx)
     FRA_TRY(ctx, host_streams_join(ctx));
     return FRA_OK;
 }
+
+#ifdef FRA_TIMELINE
+// diagnostic build only: reset (out == NULL) or read the [4][4096] timeline
+int fra_debug_timeline(unsigned long long *out)
+{
+    if (!out) {
+        static unsigned long long init[4][4096];
+        for (int s = 0; s < 4096; ++s) { init[0][s] = init[2][s] = ~0ULL; init[1][s] = init[3][s] = 0; }
+        return cudaMemcpyToSymbol(g_timeline, init, sizeof(init)) == cudaSuccess ? FRA_OK : FRA_ERR_CUDA;
+    }
+    cudaDeviceSynchronize();
+    return cudaMemcpyFromSymbol(out, g_timeline, sizeof(unsigned long long) * 4 * 4096) == cudaSuccess ? FRA_OK : FRA_ERR_CUDA;
+}
+#endif
 
 int fra_last_kernel_count(const fra_ctx *ctx) { return ctx ? ctx->last_kernels : FRA_ERR_INVALID; }
 

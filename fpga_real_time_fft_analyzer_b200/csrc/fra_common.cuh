@@ -23,6 +23,25 @@
 
 namespace fra {
 
+#ifdef FRA_TIMELINE
+// Diagnostic build only (tools/timeline_probe.py): first-CTA start and last-CTA end of every
+// window+IIR ([0], [1]) and FFT ([2], [3]) launch, by call index, in globaltimer nanoseconds.
+__device__ unsigned long long g_timeline[4][4096];
+FRA_DEV unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+FRA_DEV void timeline_mark(int row, int step)
+{
+    if (threadIdx.x == 0 && step >= 0 && step < 4096) {
+        if (row & 1) atomicMax(&g_timeline[row][step], globaltimer_ns());
+        else atomicMin(&g_timeline[row][step], globaltimer_ns());
+    }
+}
+#endif
+
 constexpr int kWindowLen = 16384;          // NEW/hann.vhd: Hann_ROM(0 to 16383)
 constexpr int kStages = 6;                 // NEW/filter_iir12_cust.vhd:68-240
 constexpr float kMagic = 12582912.0f;      // 1.5 * 2^23: ulp = 1 on [2^23, 2^24)

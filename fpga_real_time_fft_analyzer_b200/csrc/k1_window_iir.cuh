@@ -34,6 +34,9 @@ struct K1Args {
     int n;                  // samples per frame, multiple of 256
     int continuous;
     int speculate;          // k1_split: try the no-overflow recurrence first (rolled back when it was wrong)
+#ifdef FRA_TIMELINE
+    int tl_step;
+#endif
 };
 
 // ------------------------------------------------------------------ k1_lane
@@ -807,6 +810,9 @@ __global__ void __launch_bounds__(kDuoWarps * 32, 2) k1_duo(K1Args a)
     const int cc = live ? c : (a.channels - 1);
     const int n_chunks = a.n / kStageChunk;
     const int n_steps = n_chunks + kDuoPairs + 1;                 // + fill of the three pairs + the writer's last chunk
+#ifdef FRA_TIMELINE
+    timeline_mark(0, a.tl_step);
+#endif
 
     if (warp == 0) {
         duo_loader_request(a, c0, 0, smem_raw, lane);
@@ -815,6 +821,9 @@ __global__ void __launch_bounds__(kDuoWarps * 32, 2) k1_duo(K1Args a)
             duo_loader_step(a, c0, t, n_chunks, smem_raw, lane);
             __syncthreads();
         }
+#ifdef FRA_TIMELINE
+        timeline_mark(1, a.tl_step);
+#endif
     } else if (warp == kDuoWarps - 1) {
         // shares the loader's scheduler: both are short, latency-bound instruction streams
         for (int t = 0; t < n_steps; ++t) {

@@ -36,6 +36,9 @@ struct K2Args {
     int batch;
     unsigned exp23;         // 0x4B000000 as data (keeps PRMT's selector an immediate)
     int frame0;             // host side only: index of the first frame within the context (scratch offset of the 64K path)
+#ifdef FRA_TIMELINE
+    int tl_step;
+#endif
 };
 
 template <int LOG2N>
@@ -227,6 +230,9 @@ __global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS, (LOG2N == 15) ? 1 : 3
     float2 *buf = reinterpret_cast<float2 *>(smem_raw);
     const int tid = threadIdx.x;
     const int frame0 = blockIdx.x * P::FPC;
+#ifdef FRA_TIMELINE
+    timeline_mark(2, a.tl_step);
+#endif
 
     // ---------------------------------------------- radix-16 Stockham passes
 #pragma unroll 1
@@ -394,6 +400,9 @@ __global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS, (LOG2N == 15) ? 1 : 3
         const int k = (tid & 1) ? (P::L / 2) : 0;
         if (frame0 + fr < a.batch) item(fr, k, __ldg(a.twn + k));
     }
+#ifdef FRA_TIMELINE
+    timeline_mark(3, a.tl_step);
+#endif
 }
 
 // ------------------------------------------------------------------ N = 65536

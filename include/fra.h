@@ -63,7 +63,8 @@ typedef enum fra_status {
 #define FRA_K1_FORCE_LANE   0x2u     /* always use the lane-per-channel window+IIR kernel */
 #define FRA_K1_FORCE_STAGE  0x10u    /* always use the warp-per-stage pipeline window+IIR kernel */
 #define FRA_K1_FORCE_DUO    0x20u    /* always use the two-stages-per-warp pipeline window+IIR kernel */
-#define FRA_PIPELINE        0x40u    /* fra_process runs the window+IIR of call i+1 beside the FFT of call i on two
+#define FRA_PIPELINE        0x40u    /* fra_process runs the window+IIR of call i+1 beside the FFT of call i (which is
+                                        enqueued by call i+1, or by fra_join / fra_sync after the last call) on two
                                         internal streams (the FPGA does the same: the filter streams the next frame
                                         while xfft_0 unloads the previous one, dsp_system_top.vhd:530-567).  The call
                                         only waits for `cuda_stream` (inputs ready); inputs must stay untouched and
