@@ -216,10 +216,21 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # The path has no collective (channels are independent), so the only inter-rank traffic
+        # of this benchmark is its own barrier and the max over ranks: two scalars on the host.
+        # gloo by default: with an NCCL communicator alive in the process the pipelined loop ran
+        # 0.311 instead of 0.2585 ms per step on every rank (N = 2, measured), while two
+        # independent single-GPU processes side by side both ran 0.2585.  FRA_BENCH_BACKEND=nccl
+        # restores NCCL.
+        backend = os.environ.get("FRA_BENCH_BACKEND", "gloo")
+        if backend == "nccl":
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend)
     from fpga_real_time_fft_analyzer_b200 import FraContext, synth
     from fpga_real_time_fft_analyzer_b200.sharding import channel_range
     dev = torch.device("cuda", local)
+    red_dev = dev if (world > 1 and dist.get_backend() == "nccl") else torch.device("cpu")
     total_channels = CHANNELS * world                      # weak scaling: 4096 channels per GPU
     c0, c1 = channel_range(total_channels, rank, world)
     channels = c1 - c0
@@ -268,6 +279,7 @@ def run_ours(args):
     host_enqueue_ms = 1e3 * (time.perf_counter() - t_host) / args.steps      # host time to enqueue one step
     barrier()
     elapsed_ms = e0.elapsed_time(e1)
+    print(f"[bench] rank {rank}: {elapsed_ms / args.steps:.4f} ms per step on this rank", file=sys.stderr)
     # per-kernel durations: events recorded inside the library around each kernel, in one more
     # pass outside the timed region on the sequential context (each kernel alone on the GPU; in
     # the pipelined loop the two overlap and a kernel's own span is not its cost)
@@ -276,7 +288,7 @@ def run_ours(args):
         a, b = seq.profile_last()
         k1_ms.append(a); k2_ms.append(b)
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=red_dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     elapsed_ms = float(t.item())
@@ -306,7 +318,7 @@ def run_ours(args):
     _ = int(pending[0]["frames"][0, 0])
     torch.cuda.synchronize()
     e2e_ms = 1e3 * (time.perf_counter() - t0) / e2e_steps
-    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=red_dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = total_channels * N / (float(t.item()) * 1e-3) / 1e9
