@@ -57,6 +57,7 @@ SIGNATURES = {
     "fra_load_sections": (C.c_int, [C.c_void_p, C.POINTER(C.c_int8)]),
     "fra_get_sections": (C.c_int, [C.c_void_p, C.POINTER(C.c_int8)]),
     "fra_set_mode": (C.c_int, [C.c_void_p, C.c_uint8]),
+    "fra_set_mag_average": (C.c_int, [C.c_void_p, C.c_float]),
     "fra_reset": (C.c_int, [C.c_void_p]),
     "fra_get_mode": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint8)]),
     "fra_get_bank": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int8)]),

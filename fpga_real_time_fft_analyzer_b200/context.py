@@ -90,6 +90,11 @@ class FraContext:
         self._check(self._L.fra_get_sections(self._h, arr), "fra_get_sections")
         return np.array(arr[:], dtype=np.int8).reshape(6, 6)
 
+    def set_mag_average(self, alpha: float):
+        """alpha = 1: plain magnitudes; 0 < alpha < 1: the `mag` output buffer (pass the same one every
+        call via out=) holds the exponential moving average mag += alpha * (|bin| - mag)."""
+        self._check(self._L.fra_set_mag_average(self._h, C.c_float(alpha)), "fra_set_mag_average")
+
     def set_mode(self, mode: int):
         self._check(self._L.fra_set_mode(self._h, mode), "fra_set_mode")
 

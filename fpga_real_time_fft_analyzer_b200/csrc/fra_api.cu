@@ -50,6 +50,7 @@ struct fra_ctx {
     // control plane (what the RTL keeps in registers)
     uint8_t mode = FRA_MODE_BYPASS;
     uint8_t transport = FRA_CMD_ETHERNET_MODE;
+    float mag_alpha = 1.0f;          // fra_set_mag_average
     int8_t bank1[12] = {0};
     int8_t sections[6][6] = {{0}};  // fra_load_sections: six independent sections (superset of the 12-byte bank)
     bool sections_loaded = false;   // bank 1 is `sections` instead of `bank1` alternated
@@ -252,6 +253,7 @@ int launch_k2_64k(fra_ctx *ctx, const K2Args &args, bool win, int qmode, cudaStr
     o.mag = args.mag;
     o.phase = args.phase;
     o.qscale = args.qscale;
+    o.mag_alpha = args.mag_alpha;
     const size_t total = frames * kHalf64k;
     const dim3 grid((unsigned)((total + 255) / 256));
     if (qmode == 0) {
@@ -393,6 +395,7 @@ int process_range(fra_ctx *ctx, const int16_t *d_in, int c0, int nch, int contin
         k2.mag = o.d_mag;
         k2.phase = o.d_phase;
         k2.qscale = std::ldexp(0.5f, log2_scale);
+        k2.mag_alpha = ctx->mag_alpha;
         k2.batch = nch;
         k2.frame0 = c0;
 #ifdef FRA_TIMELINE
@@ -652,6 +655,13 @@ int fra_load_sections(fra_ctx *ctx, const int8_t coeff[36])
     std::memcpy(ctx->sections, coeff, 36);
     ctx->sections_loaded = true;
     ctx->n_upload++;
+    return FRA_OK;
+}
+
+int fra_set_mag_average(fra_ctx *ctx, float alpha)
+{
+    if (!ctx || !(alpha > 0.0f) || alpha > 1.0f) return FRA_ERR_INVALID;
+    ctx->mag_alpha = alpha;
     return FRA_OK;
 }
 
@@ -1127,6 +1137,7 @@ int fra_fft_only(fra_ctx *ctx, const int16_t *d_in, int batch, float *d_iq, void
     k2.mag = nullptr;
     k2.phase = nullptr;
     k2.qscale = std::ldexp(0.5f, -ctx->log2n);
+    k2.mag_alpha = 1.0f;
     k2.batch = batch;
     k2.frame0 = 0;
 #ifdef FRA_TIMELINE

@@ -33,6 +33,7 @@ struct K2Args {
     float *mag;             // [B][N] or null
     float *phase;           // [B][N] or null
     float qscale;           // 0.5 * 2^log2_scale (the untangle leaves 2 X[k])
+    float mag_alpha;        // 1: mag = |bin|; in (0, 1): mag <- mag + alpha (|bin| - mag), a running average across calls
     int batch;
     unsigned exp23;         // 0x4B000000 as data (keeps PRMT's selector an immediate)
     int frame0;             // host side only: index of the first frame within the context (scratch offset of the 64K path)
@@ -167,6 +168,7 @@ struct BinOut {
     float *mag;
     float *phase;
     float qscale;
+    float mag_alpha;
 };
 
 // One bin and its conjugate-symmetric partner: X[up + off] = p/2, X[dn + off_conj] = conj(p)/2.
@@ -192,8 +194,11 @@ FRA_DEV void emit_pair(const BinOut &o, size_t up, size_t dn, int off, int off_c
             const float fre = qre - kMagic, fim = qim - kMagic, fimc = qimc - kMagic;
             const float re2 = __fmul_rn(fre, fre);
             if (o.mag != nullptr) {
-                o.mag[up + off] = __fsqrt_rn(__fadd_rn(re2, __fmul_rn(fim, fim)));
-                if (write_conj) o.mag[dn + off_conj] = __fsqrt_rn(__fadd_rn(re2, __fmul_rn(fimc, fimc)));
+                // spectrum averaging fused into the pack stage (reference README "Contributing": waterfall /
+                // averaging display options): the caller's magnitude buffer holds the running average
+                auto put = [&](float *dst, float m) { *dst = (o.mag_alpha < 1.0f) ? __fmaf_rn(o.mag_alpha, m - *dst, *dst) : m; };
+                put(o.mag + up + off, __fsqrt_rn(__fadd_rn(re2, __fmul_rn(fim, fim))));
+                if (write_conj) put(o.mag + dn + off_conj, __fsqrt_rn(__fadd_rn(re2, __fmul_rn(fimc, fimc))));
             }
             if (o.phase != nullptr) {
                 o.phase[up + off] = atan2f(fim, fre);
@@ -320,6 +325,7 @@ __global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS, (LOG2N == 15) ? 1 : 3
     out.iq = (OUT == 0) ? nullptr : a.iq;
     out.mag = (OUT == 0) ? nullptr : a.mag;
     out.phase = (OUT == 0) ? nullptr : a.phase;
+    out.mag_alpha = a.mag_alpha;
 
     // one work item: the pair of sub-FFT bins (k, L-k) of frame `fr`, all F sub-sequences
     auto item = [&](int fr, int k, float2 wn) {
@@ -374,9 +380,14 @@ __global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS, (LOG2N == 15) ? 1 : 3
             const float2 t = cmul(w, fo);
             const float2 p = cadd(fe, t);                              // 2 X[j],     j = k + L q
             const float2 m = csub(fe, t);                              // 2 X[M + j]
-            // X[j], X[N - j] (j = 0: no partner), X[M + j], X[M - j]
-            emit_pair<QMODE>(out, up, dn, P::L * q, P::N - P::L * q, (q > 0) || (k != 0), p);
-            emit_pair<QMODE>(out, up, dn, P::M + P::L * q, P::M - P::L * q, true, m);
+            // X[j], X[N - j] (j = 0: no partner), X[M + j], X[M - j].  For the self-paired items k = 0
+            // and k = L/2 the mirrored indices are also another q's direct ones (N - j = M + j',
+            // M - j = j'); both writers run in this thread and the mirrored one keeps X[N - k] =
+            // conj(X[k]) bit-exact, so both are kept - except when the magnitude output averages,
+            // which is a read-modify-write and must touch every bin exactly once
+            const bool once = out.mag_alpha < 1.0f && (k == 0 || k == P::L / 2);
+            emit_pair<QMODE>(out, up, dn, P::L * q, P::N - P::L * q, !once && ((q > 0) || (k != 0)), p);
+            emit_pair<QMODE>(out, up, dn, P::M + P::L * q, P::M - P::L * q, !once, m);
         }
     };
 

@@ -139,6 +139,13 @@ typedef struct fra_outputs {
 int fra_process(fra_ctx *ctx, const int16_t *d_in, int continuous, int log2_scale,
                 const fra_outputs *out, void *cuda_stream);
 
+/* Spectrum averaging fused into the pack stage (the reference README lists waterfall / averaging
+ * display options under "Contributing").  alpha = 1 (default): d_mag
+ * receives |bin| as decode_mag_16iq_le computes it.  0 < alpha < 1: the buffer passed as d_mag is
+ * read and updated in place, mag <- mag + alpha (|bin| - mag), i.e. it holds an exponential moving
+ * average across calls and must be the same (initially zeroed or primed) buffer every call. */
+int fra_set_mag_average(fra_ctx *ctx, float alpha);
+
 /* The same step through host buffers: pinned staging + H2D, fra_process, D2H of
  * the requested outputs, synchronised on return.  This is the call a GpuReceiver
  * backend makes per batch of frames; h_out fields are HOST pointers. */

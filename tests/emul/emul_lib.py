@@ -65,9 +65,11 @@ class EmulFra:
         return self.L.fra_command(self.h, bytes(data), len(data))
 
     def process(self, x, continuous=False, log2_scale=_abi.FRA_SCALE_DEFAULT, want=("filtered", "frames", "iq"),
-                host=False):
+                host=False, out=None):
         x = np.ascontiguousarray(x, dtype=np.int16).reshape(self.c, self.n)
-        out = {}
+        if out is not None:
+            want = ()
+        out = {} if out is None else out
         if "filtered" in want:
             out["filtered"] = np.zeros((self.c, self.n), np.int16)
         if "frames" in want:

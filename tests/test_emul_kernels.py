@@ -82,6 +82,30 @@ def test_six_independent_sections(flags, rom):
         f.close()
 
 
+def test_magnitude_averaging_in_the_pack_stage(rom):
+    """fra_set_mag_average: the caller's magnitude buffer holds an exponential moving average."""
+    rng = np.random.default_rng(9)
+    c, n, alpha = 3, 1024, 0.25
+    f = EmulFra(c, n)
+    try:
+        assert f.L.fra_set_mag_average(f.h, 0.0) != 0 and f.L.fra_set_mag_average(f.h, 1.5) != 0
+        assert f.L.fra_set_mag_average(f.h, alpha) == 0
+        out = {"mag": np.zeros((c, n), np.float32), "frames": np.zeros((c, 4 * n), np.uint8)}
+        avg = np.zeros((c, n), np.float32)
+        for frame in range(4):
+            x = adversarial(rng, c, n)
+            f.process(x, out=out)
+            _, _, mag = g.decode_frame(out["frames"])
+            avg = (avg + np.float32(alpha) * (mag.astype(np.float32) - avg)).astype(np.float32)
+            assert np.allclose(out["mag"], avg, rtol=1e-6, atol=1e-4)
+        assert f.L.fra_set_mag_average(f.h, 1.0) == 0
+        f.process(x, out=out)
+        _, _, mag = g.decode_frame(out["frames"])
+        assert np.array_equal(out["mag"].view(np.uint32), mag.astype(np.float32).view(np.uint32))
+    finally:
+        f.close()
+
+
 def test_pipeline_flag_same_results(rom):
     """FRA_PIPELINE only changes which streams the kernels go to: the host logic around it
     (two scratch buffers, hand-over events) must leave results and state unchanged."""

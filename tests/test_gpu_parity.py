@@ -383,3 +383,21 @@ def test_64k_frames_full_chain(fra, rom):
         assert np.array_equal(mag.view(np.uint32), out["mag"].view(np.uint32))
         host = ctx.process_host(torch.from_numpy(x).pin_memory(), want=("frames",))
         assert np.array_equal(host["frames"].numpy(), out["frames"])
+
+
+def test_magnitude_averaging_in_the_pack_stage(fra, rom):
+    rng = np.random.default_rng(19)
+    c, n, alpha = 9, 16384, 0.125
+    with fra.FraContext(c, n) as ctx:
+        ctx.command(0x00)
+        ctx.set_mag_average(alpha)
+        out = {"mag": torch.zeros((c, n), dtype=torch.float32, device="cuda"),
+               "frames": torch.empty((c, 4 * n), dtype=torch.uint8, device="cuda")}
+        avg = np.zeros((c, n), np.float32)
+        for frame in range(3):
+            ctx.process(dev(adversarial(rng, c, n)), continuous=frame > 0, out=out)
+            _, _, mag = g.decode_frame(out["frames"].cpu().numpy())
+            avg = (avg + np.float32(alpha) * (mag.astype(np.float32) - avg)).astype(np.float32)
+            assert np.allclose(out["mag"].cpu().numpy(), avg, rtol=1e-6, atol=1e-4)
+        with pytest.raises(fra.FraError):
+            ctx.set_mag_average(0.0)
