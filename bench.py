@@ -216,13 +216,14 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
-        # The path has no collective (channels are independent), so the only inter-rank traffic
-        # of this benchmark is its own barrier and the max over ranks: two scalars on the host.
-        # gloo by default: with an NCCL communicator alive in the process the pipelined loop ran
-        # 0.311 instead of 0.2585 ms per step on every rank (N = 2, measured), while two
-        # independent single-GPU processes side by side both ran 0.2585.  FRA_BENCH_BACKEND=nccl
-        # restores NCCL.
-        backend = os.environ.get("FRA_BENCH_BACKEND", "gloo")
+        # The path has no collective (channels are independent): the only inter-rank traffic of
+        # this benchmark is its own barrier and the max over ranks.  NCCL's NVLS (NVLink SHARP
+        # multicast) set-up is switched off for it: with NVLS initialised in the process the
+        # pipelined loop ran 0.312 instead of 0.270 ms per step on every rank (N = 2, measured;
+        # NCCL_CUMEM_ENABLE=0 has the same effect, P2P off or fewer channels do not), and a scalar
+        # max has no use for in-switch reduction.  FRA_BENCH_BACKEND=gloo avoids NCCL altogether.
+        os.environ.setdefault("NCCL_NVLS_ENABLE", "0")
+        backend = os.environ.get("FRA_BENCH_BACKEND", "nccl")
         if backend == "nccl":
             dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         else:
