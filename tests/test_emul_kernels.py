@@ -122,9 +122,39 @@ def test_pipeline_flag_same_results(rom):
             assert np.array_equal(out["filtered"], y)
             out2 = f.process(x, continuous=False, want=("frames",))       # library-owned scratch, alternating
             y0, st = cg.window_iir(x, rom, 0x00, g.BANK0_COEFF, B1, None)
-            assert np.array_equal(f.get_state(), st)
+            assert np.array_equal(f.get_state(), st)                      # joins: the held-back FFT is flushed
+            seq = EmulFra(c, n)
+            try:
+                seq.command(bytes([0x00]))
+                ref = seq.process(x, continuous=False, want=("frames",))
+            finally:
+                seq.close()
+            assert np.array_equal(out2["frames"], ref["frames"])
+            # the host-buffer call on a pipelined context drains the pipeline first
+            out3 = f.process(x, continuous=False, want=("frames", "filtered"), host=True)
+            assert np.array_equal(out3["frames"], ref["frames"]) and np.array_equal(out3["filtered"], y0)
     finally:
         f.close()
+
+
+def test_pipeline_flag_64k_frames(rom):
+    """FRA_PIPELINE with the three-kernel 64K FFT path as the held-back launch."""
+    rng = np.random.default_rng(6)
+    c, n = 2, 65536
+    f, seq = EmulFra(c, n, _abi.FRA_PIPELINE), EmulFra(c, n)
+    try:
+        f.command(bytes([0x00])); seq.command(bytes([0x00]))
+        outs, refs = [], []
+        for frame in range(2):
+            x = adversarial(rng, c, n)
+            outs.append(f.process(x, continuous=frame > 0, want=("frames",)))
+            refs.append(seq.process(x, continuous=frame > 0, want=("frames",)))
+        assert f.L.fra_join(f.h, None) == 0
+        for o, r in zip(outs, refs):
+            assert np.array_equal(o["frames"], r["frames"])
+        assert np.array_equal(f.get_state(), seq.get_state())
+    finally:
+        f.close(); seq.close()
 
 
 def test_k1_random_coefficients_and_user_state(rom):
