@@ -3,14 +3,16 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-A step = one pass of the hot path over one batch: 4096 channels x 16384 int16 samples
-per GPU (BASELINE config 2), fixed filter bank 0 selected (command byte 0x00), frames
-independent, output = the reference's 65536-byte int16 I/Q frame per channel.  N > 1
-(torchrun, one rank per GPU) shards channels: every rank runs its own 4096 channels,
-no data-path collective ("weak" scaling).  `value` has inputs resident in HBM; `e2e`
-is the same metric through FraContext.process_host with pinned HOST buffers, H2D and
-D2H inside the timed region.  --impl reference times the repo's CPU path
-(numpy/scipy float chain, oracle/golden.py:cpu_float_chain) on all host cores.
+Headline workload = BASELINE config 3: 65536 CONTINUOUS channels x 16384-sample frames, IIR
+history carried from step to step, fixed filter bank 0 (command byte 0x00), output = the
+reference's 65536-byte int16 I/Q frame per channel.  The 65536 channels are sharded over the N
+GPUs (65536 / N each, "strong" scaling; N = 1 runs all of them), no data-path collective.
+A step = every channel's next frame.  `value` has inputs resident in HBM; `e2e` is the same
+metric through FraContext.process_host_async with pinned HOST buffers, H2D and D2H inside the
+timed region.  Beside the K-step burst the line carries `sustained` (the same loop for >= 1 s)
+and `config2` (BASELINE config 2: 4096 independent channels per GPU, history reset per frame).
+--impl reference times the repo's CPU path (numpy/scipy float chain with the filter history
+carried, oracle/golden.py:cpu_float_chain) on all host cores.
 """
 from __future__ import annotations
 
@@ -47,11 +49,14 @@ def emit(line):
     out.write(json.dumps(line) + "\n")
     out.flush()
 
-CHANNELS = 4096
+TOTAL_CHANNELS = 65536          # BASELINE config 3: continuous channels, sharded over the GPUs
+CONFIG2_CHANNELS = 4096         # BASELINE config 2: independent channels per GPU
 N = 16384
 METRIC = "Gsamples/s window+IIR12+16K FFT"
 UNIT = "Gsamples/s"
 B_ALG = {"chain": 6.0, "window_iir": 4.0, "fft_pack": 6.0}     # algorithmic HBM bytes per sample
+WORKLOAD = ("BASELINE config 3: 65536 continuous channels x 16384-sample frames (IIR history carried), "
+            "window + IIR12 (bank 0) + 16K FFT -> int16 I/Q frames, channels sharded 65536/N per GPU")
 
 
 def measured_peak():
@@ -67,6 +72,8 @@ _CPU_CACHE = {}
 
 
 def _cpu_worker(args):
+    """One process's share of a CPU step: `channels` continuous channels, one 16384-sample frame
+    each, the filter history (sosfilt's zi) carried from the previous call as in config 3."""
     seed, channels, reps = args
     import numpy as np
     from oracle import golden as g
@@ -74,11 +81,13 @@ def _cpu_worker(args):
         _CPU_CACHE["rom"] = np.fromfile(os.path.join(ROOT, "tests", "golden", "hann_rom.i16"), dtype="<i2")
     rom = _CPU_CACHE["rom"]
     if channels not in _CPU_CACHE:                        # inputs are made once, outside the timed calls
-        _CPU_CACHE[channels] = g.tone_noise(range(seed * channels, (seed + 1) * channels), n=N, seed=seed)
-    x = _CPU_CACHE[channels]
+        _CPU_CACHE[channels] = [g.tone_noise(range(seed * channels, (seed + 1) * channels), n=N, seed=seed),
+                                np.zeros((6, channels, 2))]
+    x, zi = _CPU_CACHE[channels]
     t0 = time.perf_counter()
     for _ in range(reps):
-        g.cpu_float_chain(x, g.BANK0_COEFF, rom)
+        _, _, zi = g.cpu_float_chain(x, g.BANK0_COEFF, rom, zi)
+    _CPU_CACHE[channels][1] = zi
     return time.perf_counter() - t0
 
 
@@ -88,7 +97,7 @@ MIN_WARMUP = 10         # untimed steps actually run before the timed loop (the 
 
 def cpu_float_rate(cores, channels_per_proc, reps):
     """Gsamples/s of the numpy/scipy chain with `cores` processes, each filtering
-    `reps` batches of `channels_per_proc` x 16384 samples."""
+    `reps` frames of `channels_per_proc` x 16384 samples."""
     import multiprocessing as mp
     ctx = mp.get_context("spawn")
     with ctx.Pool(cores) as pool:
@@ -100,16 +109,18 @@ def cpu_float_rate(cores, channels_per_proc, reps):
     return samples / dt / 1e9, samples, dt
 
 
-def profiled_traffic(kernel):
-    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` summary
-    (profiles/r01_<kernel>_4096ch.txt, the same 4096-channel launch), or None."""
-    path = os.path.join(ROOT, "profiles", f"r01_{kernel}_4096ch.txt")
-    try:
-        for ln in open(path):
-            if ln.startswith("traffic = dram read + write per launch"):
-                return {"bytes": float(ln.split()[8]) * 1e6, "source": os.path.relpath(path, ROOT)}
-    except (OSError, ValueError, IndexError):
-        pass
+def profiled_traffic(kernel, channels):
+    """DRAM bytes per launch of `kernel` from a committed `ncu --set full` summary of a launch
+    with the same channel count (profiles/r*_<kernel>_<channels>ch.txt, newest round first), or None."""
+    import glob
+    paths = sorted(glob.glob(os.path.join(ROOT, "profiles", f"r*_{kernel}_{channels}ch.txt")), reverse=True)
+    for path in paths:
+        try:
+            for ln in open(path):
+                if ln.startswith("traffic = dram read + write per launch"):
+                    return {"bytes": float(ln.split()[8]) * 1e6, "source": os.path.relpath(path, ROOT)}
+        except (OSError, ValueError, IndexError):
+            pass
     return None
 
 
@@ -145,11 +156,12 @@ def run_reference(args):
     samples = cores * per_step_channels * N
     ms = 1e3 * sum(rates) / len(rates)
     value = samples / (ms * 1e-3) / 1e9
-    sample = f"{cores} processes x {per_step_channels} channels x {N} samples per step (bounded sample of the 4096-channel workload)"
+    sample = (f"{cores} processes x {per_step_channels} continuous channels x {N} samples per step "
+              f"(bounded sample of the 65536-channel workload; filter history carried between steps)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "BASELINE config 2: 4096 ch x 16384, window+IIR12 (bank 0)+16K FFT; numpy/scipy float chain"},
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD + "; CPU arm: numpy window, scipy sosfilt (zi carried), np.fft.fft, float64"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -206,6 +218,25 @@ class ClockSampler:
                 "samples": len(self.sm)}
 
 
+def timed_loop(torch, ctx, xs, out, steps, continuous, barrier):
+    """`steps` calls of ctx.process between two CUDA events on the launching (current) stream; the
+    end event sits behind ctx.join(), so every step's FFT has finished inside the timed region.
+    Returns (elapsed ms, kernels launched, host seconds spent enqueueing)."""
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    barrier()
+    e0.record()
+    t_host = time.perf_counter()
+    for i in range(steps):
+        ctx.process(xs[i % len(xs)], continuous=continuous, want=("frames",), out=out)
+        launches += ctx.last_kernel_count
+    ctx.join()                                             # the current stream waits for both internal streams
+    e1.record()
+    host_s = time.perf_counter() - t_host
+    barrier()
+    return e0.elapsed_time(e1), launches, host_s
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -228,101 +259,131 @@ def run_ours(args):
             dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         else:
             dist.init_process_group(backend)
-    from fpga_real_time_fft_analyzer_b200 import FraContext, synth
+    from fpga_real_time_fft_analyzer_b200 import FraContext, _abi, synth
     from fpga_real_time_fft_analyzer_b200.sharding import channel_range
     dev = torch.device("cuda", local)
     red_dev = dev if (world > 1 and dist.get_backend() == "nccl") else torch.device("cpu")
-    total_channels = CHANNELS * world                      # weak scaling: 4096 channels per GPU
-    c0, c1 = channel_range(total_channels, rank, world)
-    channels = c1 - c0
 
-    from fpga_real_time_fft_analyzer_b200 import _abi
-    # FRA_PIPELINE: the FFT of step i runs beside the window+IIR of step i+1 (two internal
-    # streams, as the FPGA overlaps filter and xfft_0); every step's work completes inside the
-    # timed region because the end event is recorded behind ctx.join()
-    ctx = FraContext(channels, N, device=local, flags=_abi.FRA_PIPELINE)
-    ctx.command(0x00)                                      # FILTER_DEFAULT_CMD: fixed 12th-order bank 0
-    seq = FraContext(channels, N, device=local)            # sequential twin: per-kernel durations, e2e
-    seq.command(0x00)
-    n_buf = 3                                              # rotate inputs; working set/step = 512 MiB >> 126 MB L2
-    xs = [synth.tone_noise(channels, N, dev, first_channel=c0, frame=i) for i in range(n_buf)]
-    out = {"frames": torch.empty((channels, 4 * N), dtype=torch.uint8, device=dev)}
-    seq.profile(True)
+    def max_over_ranks(v):
+        t = torch.tensor([v], dtype=torch.float64, device=red_dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-    def barrier():
-        ctx.sync()
+    def sum_over_ranks(v):
+        t = torch.tensor([v], dtype=torch.float64, device=red_dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def barrier(*ctxs):
+        for c in ctxs:
+            c.sync()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
 
-    def step(i):
-        ctx.process(xs[i % n_buf], continuous=False, want=("frames",), out=out)
+    # ---- headline: config 3, this rank's share of the 65536 continuous channels
+    c0, c1 = channel_range(TOTAL_CHANNELS, rank, world)
+    channels = c1 - c0
+    pipe_flag = 0 if os.environ.get("FRA_BENCH_SEQUENTIAL") else _abi.FRA_PIPELINE
+    # FRA_PIPELINE: the FFT of step i runs beside the window+IIR of step i+1 (two internal
+    # streams, as the FPGA overlaps filter and xfft_0); every step's work completes inside the
+    # timed region because the end event is recorded behind ctx.join()
+    ctx = FraContext(channels, N, device=local, flags=pipe_flag)
+    ctx.command(0x00)                                      # FILTER_DEFAULT_CMD: fixed 12th-order bank 0
+    n_buf = 3                                              # rotating inputs: consecutive frames of every channel's stream
+    xs = [synth.tone_noise(channels, N, dev, first_channel=c0, frame=i) for i in range(n_buf)]
+    out = {"frames": torch.empty((channels, 4 * N), dtype=torch.uint8, device=dev)}
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.05)                                   # NVML initialised before the GPU gets busy
     warmup_run = max(args.warmup, MIN_WARMUP)
-    for i in range(warmup_run):
-        step(i)
-    k1_ms, k2_ms = [], []
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches = 0
-    barrier()
-    e0.record()
-    t_host = time.perf_counter()
-    for i in range(args.steps):
-        step(i)
-        launches += ctx.last_kernel_count
-    ctx.join()                                             # the current stream waits for both internal streams
-    e1.record()
-    host_enqueue_ms = 1e3 * (time.perf_counter() - t_host) / args.steps      # host time to enqueue one step
-    barrier()
-    elapsed_ms = e0.elapsed_time(e1)
-    print(f"[bench] rank {rank}: {elapsed_ms / args.steps:.4f} ms per step on this rank", file=sys.stderr)
-    # per-kernel durations: events recorded inside the library around each kernel, in one more
-    # pass outside the timed region on the sequential context (each kernel alone on the GPU; in
-    # the pipelined loop the two overlap and a kernel's own span is not its cost)
-    for i in range(min(args.steps, 10)):
-        seq.process(xs[i % n_buf], continuous=False, want=("frames",), out=out)
-        a, b = seq.profile_last()
-        k1_ms.append(a); k2_ms.append(b)
+    ctx.process(xs[0], continuous=False, want=("frames",), out=out)          # the stream starts: history zero
+    for i in range(1, warmup_run):
+        ctx.process(xs[i % n_buf], continuous=True, want=("frames",), out=out)
+    elapsed_ms, launches, host_s = timed_loop(torch, ctx, xs, out, args.steps, True, lambda: barrier(ctx))
+    print(f"[bench] rank {rank}: {elapsed_ms / args.steps:.4f} ms per step on this rank ({channels} channels)", file=sys.stderr)
+    ms_per_step = max_over_ranks(elapsed_ms) / args.steps
+    value = TOTAL_CHANNELS * N / (ms_per_step * 1e-3) / 1e9
+    host_enqueue_ms = 1e3 * host_s / args.steps
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=red_dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(t.item())
-    ms_per_step = elapsed_ms / args.steps
-    value = total_channels * N / (ms_per_step * 1e-3) / 1e9
 
-    # ---- e2e: host buffers through the public API, copies inside the timed region
+    # ---- the same loop for >= 1 s: a burst of K steps says nothing about the power-capped steady state
+    sus_steps = max(args.steps, int(1.2e3 / max(ms_per_step, 1e-3)) + 1)
+    sampler2 = ClockSampler(local)
+    if rank == 0:
+        sampler2.start()
+    sus_ms, _, _ = timed_loop(torch, ctx, xs, out, sus_steps, True, lambda: barrier(ctx))
+    sus_ms_per_step = max_over_ranks(sus_ms) / sus_steps
+    sus_clocks = sampler2.stop() if rank == 0 else None
+    sustained = {"steps": sus_steps, "seconds": sus_ms_per_step * sus_steps * 1e-3, "ms_per_step": sus_ms_per_step,
+                 "value": TOTAL_CHANNELS * N / (sus_ms_per_step * 1e-3) / 1e9, "unit": UNIT, "clocks": sus_clocks}
+    ctx.close()
+
+    # ---- per-kernel durations: events recorded inside the library around each kernel on a sequential
+    # context of the same size (each kernel alone on the GPU; in the pipelined loop the two overlap
+    # and a kernel's own span is not its cost)
+    seq = FraContext(channels, N, device=local)
+    seq.command(0x00)
+    seq.profile(True)
+    k1_ms, k2_ms = [], []
+    for i in range(2 + min(args.steps, 10)):
+        seq.process(xs[i % n_buf], continuous=i > 0, want=("frames",), out=out)
+        a, b = seq.profile_last()
+        if i >= 2:
+            k1_ms.append(a); k2_ms.append(b)
+    seq.profile(False)
+
+    # ---- e2e: host buffers through the public API, copies inside the timed region.  The receiver loop
+    # of a streaming client: frame i+1 is uploaded while frame i is still downloading
+    # (fra_process_host_async, two calls in flight); every step's input crosses PCIe and every step's
+    # frames are read on the host inside the timed region.
+    del out
     x_host = [xs[i].cpu().pin_memory() for i in range(2)]
-    pipe_ctx, ctx = ctx, seq
-    for i in range(4):                                     # warm-up: both pinned output sets get allocated here
-        _, tk = ctx.process_host_async(x_host[i % 2], want=("frames",))
-        ctx.host_wait(tk)
-    barrier()
-    t0 = time.perf_counter()
+    del xs
+    torch.cuda.empty_cache()
+    for i in range(3):                                     # warm-up: both pinned output sets get allocated here
+        _, tk = seq.process_host_async(x_host[i % 2], continuous=i > 0, want=("frames",))
+        seq.host_wait(tk)
+    barrier(seq)
     e2e_steps = max(3, min(args.steps, 10))
-    # the receiver loop of a streaming client: frame i+1 is uploaded while frame i is still
-    # downloading (fra_process_host_async, two calls in flight); every step's input crosses
-    # PCIe and every step's frames are read on the host inside the timed region
+    t0 = time.perf_counter()
     pending = None
     for i in range(e2e_steps):
-        cur = ctx.process_host_async(x_host[i % 2], want=("frames",))
+        cur = seq.process_host_async(x_host[i % 2], continuous=True, want=("frames",))
         if pending is not None:
-            ctx.host_wait(pending[1])
+            seq.host_wait(pending[1])
             _ = int(pending[0]["frames"][0, 0])              # touch the result on the host
         pending = cur
-    ctx.host_wait(pending[1])
+    seq.host_wait(pending[1])
     _ = int(pending[0]["frames"][0, 0])
     torch.cuda.synchronize()
-    e2e_ms = 1e3 * (time.perf_counter() - t0) / e2e_steps
-    t = torch.tensor([e2e_ms], dtype=torch.float64, device=red_dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = total_channels * N / (float(t.item()) * 1e-3) / 1e9
+    e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0) / e2e_steps)
+    e2e_value = TOTAL_CHANNELS * N / (e2e_ms * 1e-3) / 1e9
+    # aggregate host-link traffic of all ranks during the e2e loop (every rank shares one host)
+    host_gbs = sum_over_ranks(channels * N * 6 / (e2e_ms * 1e-3) / 1e9)
+    seq.close()
+    del x_host, pending, cur
+    seq._pinned = {}
+
+    # ---- second key: BASELINE config 2 (4096 independent channels per GPU, history reset every frame)
+    c2 = FraContext(CONFIG2_CHANNELS, N, device=local, flags=pipe_flag)
+    c2.command(0x00)
+    xs2 = [synth.tone_noise(CONFIG2_CHANNELS, N, dev, first_channel=rank * CONFIG2_CHANNELS, frame=i) for i in range(n_buf)]
+    out2 = {"frames": torch.empty((CONFIG2_CHANNELS, 4 * N), dtype=torch.uint8, device=dev)}
+    for i in range(max(warmup_run, 50)):                   # the pipelined loop settles during its first steps
+        c2.process(xs2[i % n_buf], continuous=False, want=("frames",), out=out2)
+    c2_steps = max(args.steps, 200)
+    c2_ms, _, _ = timed_loop(torch, c2, xs2, out2, c2_steps, False, lambda: barrier(c2))
+    c2_ms_per_step = max_over_ranks(c2_ms) / c2_steps
+    c2.close()
+    config2 = {"workload": f"BASELINE config 2: {CONFIG2_CHANNELS} independent channels x {N} per GPU (weak scaling), history reset per frame",
+               "steps": c2_steps, "ms_per_step": c2_ms_per_step,
+               "value": world * CONFIG2_CHANNELS * N / (c2_ms_per_step * 1e-3) / 1e9, "unit": UNIT}
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -336,11 +397,12 @@ def run_ours(args):
                 kernels[name] = {"ms": ms, "achieved_gbs": ach, "frac": ach / peak,
                                  "alg_bytes_per_sample": B_ALG[name]}
         dom = "window_iir" if k1 >= k2 else "fft_pack"
-        traffic = profiled_traffic("k1_duo" if dom == "window_iir" else "k2_fft")
-        roofline = {"bound": "hbm", "kernel": ("k1_duo<true,true,true>" if dom == "window_iir" else "k2_fft<14,false,0,0>"),
+        traffic = profiled_traffic("k1" if dom == "window_iir" else "k2_fft", channels)
+        roofline = {"bound": "hbm", "kernel": ("window+IIR12 (k1)" if dom == "window_iir" else "k2_fft<14,false,0,0>"),
                     "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                     "frac": kernels[dom]["frac"], "traffic": traffic["bytes"] if traffic else None,
                     "traffic_source": traffic["source"] if traffic else None, "peak_source": peak_src,
+                    "samples_per_launch": samples_per_launch,
                     "kernels": kernels, "sequential_ms_per_step": k1 + k2,
                     "chain": {"achieved": value / world * B_ALG["chain"], "frac": value / world * B_ALG["chain"] / peak,
                               "alg_bytes_per_sample": B_ALG["chain"]},
@@ -348,32 +410,34 @@ def run_ours(args):
         cores = os.cpu_count() or 1
         cpu_val, cpu_samples, cpu_dt = cpu_float_rate(cores, 64, CPU_REPS)     # ~1.5 s wall, ~20 core-seconds
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "int16 (window+IIR, exact on the fp32 pipe) + f32 (FFT)",
                 "data": "synthetic",
-                "config": {"workload": f"BASELINE config 2: {CHANNELS} channels x {N} samples per GPU, window + IIR12 (bank 0) + 16K FFT -> int16 I/Q frames",
-                           "channels_per_gpu": channels, "fft_size": N, "mode": "0x00",
-                           "l2": "3 rotating inputs; 512 MiB touched per step > 126 MB L2",
-                           "pipeline": "FFT of step i overlaps window+IIR of step i+1 (FRA_PIPELINE); sequential: see roofline.sequential_ms_per_step"},
+                "config": {"workload": WORKLOAD, "total_channels": TOTAL_CHANNELS,
+                           "channels_per_gpu": channels, "fft_size": N, "mode": "0x00", "continuous": True,
+                           "l2": f"3 rotating inputs; {channels * N * 8 / 2**20:.0f} MiB touched per step > 126 MB L2",
+                           "pipeline": ("FFT of step i overlaps window+IIR of step i+1 (FRA_PIPELINE)" if pipe_flag else "sequential")
+                                       + "; per-kernel times: roofline.kernels"},
                 "roofline": roofline,
+                "sustained": sustained,
+                "config2": config2,
                 "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
-                                 "sample": f"numpy/scipy float64 chain, {cores} processes x {CPU_REPS} x 64 channels x {N} samples ({cpu_dt:.1f} s wall, {cpu_dt * cores:.0f} core-seconds)",
+                                 "sample": f"numpy/scipy float64 chain (history carried), {cores} processes x {CPU_REPS} x 64 channels x {N} samples ({cpu_dt:.1f} s wall, {cpu_dt * cores:.0f} core-seconds)",
                                  "int_golden_1core": cpu_int_rate()},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": channels * N * 2,
-                        "d2h_bytes_per_step": channels * N * 4, "steps": e2e_steps},
+                        "d2h_bytes_per_step": channels * N * 4, "steps": e2e_steps,
+                        "host_link_gbs_all_ranks": host_gbs},
                 "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms, "warmup_steps_run": warmup_run, "clocks": clocks}
         emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    ctx.close()
-    pipe_ctx.close()
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()

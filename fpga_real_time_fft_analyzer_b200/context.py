@@ -31,6 +31,8 @@ class FraContext:
         self._L = lib()
         self._h = C.c_void_p()
         self.channels, self.n, self.device = int(channels), int(fft_size), int(device)
+        self.flags = int(flags)
+        self._pipe_keep = []              # FRA_PIPELINE: (x, out) of calls whose kernels may still be running
         self._async_calls = 0
         self._keep_alive = None
         rc = self._L.fra_create(C.byref(self._h), self.device, self.channels, self.n, flags)
@@ -147,7 +149,13 @@ class FraContext:
 
     def process(self, x, continuous=False, log2_scale=None, want=("frames",), out=None):
         """One step on device tensors.  x: int16 [C, N] on this context's GPU.
-        Enqueued on torch's current stream; returns {name: tensor}."""
+        Enqueued on torch's current stream; returns {name: tensor}.
+
+        FRA_PIPELINE contexts: the kernels run on the library's two internal streams (they only
+        wait for the current stream at the time of the call) and the FFT of this call is enqueued
+        by the NEXT call, join() or sync().  The returned tensors are complete only after join()
+        (device-side) or sync() (host-side); until then the context keeps x and the outputs alive,
+        so that torch's caching allocator cannot hand their memory to someone else."""
         torch = _torch()
         if not (x.is_cuda and x.dtype == torch.int16 and x.is_contiguous()
                 and x.numel() == self.channels * self.n and x.device.index == self.device):
@@ -159,6 +167,8 @@ class FraContext:
         ls = _abi.FRA_SCALE_DEFAULT if log2_scale is None else int(log2_scale)
         self._check(self._L.fra_process(self._h, x.data_ptr(), int(bool(continuous)), ls, C.byref(o),
                                         C.c_void_p(stream)), "fra_process")
+        if self.flags & _abi.FRA_PIPELINE:
+            self._pipe_keep.append((x, out))
         return out
 
     def pinned(self, name, shape, dtype):
@@ -270,6 +280,7 @@ class FraContext:
     def sync(self):
         """Host waits for everything the context has enqueued."""
         self._check(self._L.fra_sync(self._h), "fra_sync")
+        self._pipe_keep.clear()
 
     def join(self):
         """FRA_PIPELINE contexts: torch's current stream waits (on the device) for all work
@@ -277,6 +288,9 @@ class FraContext:
         import torch
         stream = torch.cuda.current_stream(self.device).cuda_stream
         self._check(self._L.fra_join(self._h, C.c_void_p(stream)), "fra_join")
+        # the current stream is now ordered behind every internal kernel: a tensor released here
+        # is recycled by the caching allocator in stream order, i.e. after those kernels
+        self._pipe_keep.clear()
 
     @property
     def last_kernel_count(self) -> int:

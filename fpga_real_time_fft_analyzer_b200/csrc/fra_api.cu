@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <utility>
 #include <vector>
 
 namespace {
@@ -98,6 +99,9 @@ struct fra_ctx {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // K1 begin/end, K2 begin/end
     bool ev_k1 = false, ev_k2 = false;
 
+    // kernels whose dynamic shared-memory limit has been raised (once per context, not per launch)
+    std::vector<std::pair<const void *, int>> smem_set;
+
     int last_kernels = 0;
     char err[256] = {0};
 };
@@ -114,6 +118,24 @@ int fail_cuda(fra_ctx *ctx, cudaError_t e, const char *what)
     do {                                                           \
         cudaError_t e_ = (expr);                                   \
         if (e_ != cudaSuccess) return fail_cuda((ctx), e_, #expr); \
+    } while (0)
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per kernel and context
+template <class K>
+int ensure_smem(fra_ctx *ctx, K kfn, int bytes)
+{
+    const void *key = reinterpret_cast<const void *>(kfn);
+    for (auto &e : ctx->smem_set)
+        if (e.first == key && e.second >= bytes) return FRA_OK;
+    FRA_TRY(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    ctx->smem_set.emplace_back(key, bytes);
+    return FRA_OK;
+}
+
+#define FRA_SMEM(ctx, kfn, bytes)                       \
+    do {                                                \
+        int rc_ = ensure_smem((ctx), (kfn), (bytes));   \
+        if (rc_ != FRA_OK) return rc_;                  \
     } while (0)
 
 StageCoef make_stage(const int8_t *k)       // k = B0,B1,B2,A0,A1 (NEW/filter_iir_cust.vhd:104-108)
@@ -179,7 +201,7 @@ int launch_k2_inst(fra_ctx *ctx, const K2Args &args, cudaStream_t st)
     // frames-only is the hot configuration and gets its own instantiation
     const bool frames_only = args.frames && !args.iq && !args.mag && !args.phase;
     auto kfn = frames_only ? k2_fft<LOG2N, WIN, QMODE, 0> : k2_fft<LOG2N, WIN, QMODE, 1>;
-    FRA_TRY(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, P::SMEM_BYTES));
+    FRA_SMEM(ctx, kfn, P::SMEM_BYTES);
     const int grid = (args.batch + P::FPC - 1) / P::FPC;
     if (grid > 0) {
         FRA_LAUNCH(kfn, dim3(grid), dim3(P::THREADS), (size_t)P::SMEM_BYTES, st, args);
@@ -348,19 +370,19 @@ int process_range(fra_ctx *ctx, const int16_t *d_in, int c0, int nch, int contin
                 k1_duo<false, false, true>,  k1_duo<true, false, true>,  k1_duo<false, true, true>,  k1_duo<true, true, true>};
             auto kfn = table[(b1z ? 1 : 0) | (fast ? 2 : 0) | (alt ? 4 : 0)];
             static_assert(kDuoSmemRequest >= kDuoSmemBytes, "k1_duo shared memory");
-            FRA_TRY(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kDuoSmemRequest));
+            FRA_SMEM(ctx, kfn, kDuoSmemRequest);
             FRA_LAUNCH(kfn, dim3(grid), dim3(kDuoWarps * 32), (size_t)kDuoSmemRequest, st, k1);
         } else if (variant == 2) {
             const int grid = (nch + 31) / 32;
             auto kfn = b1z ? k1_stage<true> : k1_stage<false>;
-            FRA_TRY(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageSmemBytes));
+            FRA_SMEM(ctx, kfn, kStageSmemBytes);
             FRA_LAUNCH(kfn, dim3(grid), dim3(kStageWarps * 32), (size_t)kStageSmemBytes, st, k1);
         } else if (variant == 1) {
             const int per_cta = kSplitWarps * kSplitGroups;
             const int grid = (nch + per_cta - 1) / per_cta;
             const size_t smem = (size_t)kSplitWarps * kSplitSmemPerWarp;
             auto kfn = k1_split;
-            FRA_TRY(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            FRA_SMEM(ctx, kfn, (int)smem);
             FRA_LAUNCH(kfn, dim3(grid), dim3(kSplitWarps * 32), smem, st, k1);
         } else {
             const int grid = (nch + kLaneBlock - 1) / kLaneBlock;
@@ -574,6 +596,20 @@ int fra_create(fra_ctx **out, int device, int n_channels, int fft_size, unsigned
         cudaMemcpy(ctx->d_twn, twn.data(), twn.size() * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemset(ctx->d_state, 0, (size_t)n_channels * 24 * sizeof(int16_t)) != cudaSuccess)
         return bail(FRA_ERR_CUDA);
+    // Work buffers are sized here, not in the first fra_process call: the filter-output scratch
+    // (two of them in pipelined mode) and, for 64K frames, the even/odd split and its fp32 halves.
+    {
+        const size_t frame_elems = (size_t)n_channels * n;
+        const size_t want_elems = frame_elems * ((flags & FRA_PIPELINE) ? 2 : 1);
+        if (cudaMalloc((void **)&ctx->d_scratch, want_elems * sizeof(int16_t)) != cudaSuccess) return bail(FRA_ERR_NOMEM);
+        ctx->scratch_elems = want_elems;
+        if (n > n_kernel) {
+            if (cudaMalloc((void **)&ctx->d_split, (size_t)n_channels * 2 * kHalf64k * sizeof(int16_t)) != cudaSuccess ||
+                cudaMalloc((void **)&ctx->d_halves, (size_t)n_channels * 2 * kHalf64k * sizeof(float2)) != cudaSuccess)
+                return bail(FRA_ERR_NOMEM);
+            ctx->split_frames = (size_t)n_channels;
+        }
+    }
     *out = ctx;
     return FRA_OK;
 }
@@ -801,11 +837,13 @@ int fra_join(fra_ctx *ctx, void *cuda_stream)
     cudaStream_t st = (cudaStream_t)cuda_stream;
     int rc = pipe_flush_fft(ctx);
     if (rc != FRA_OK) return rc;
-    // pipe_k2 is in order, so its newest event covers every earlier call; the window+IIR kernel of
-    // the last call finished before that call's FFT started.  (A call without FFT outputs leaves
-    // only its window+IIR event.)
-    FRA_TRY(ctx, cudaStreamWaitEvent(st, ctx->pipe_k1_done[(ctx->pipe_calls - 1) & 1], 0));
-    FRA_TRY(ctx, cudaStreamWaitEvent(st, ctx->pipe_k2_done[(ctx->pipe_calls - 1) & 1], 0));
+    // Both parities of both event pairs: the last call may have asked for no FFT output, in which
+    // case the newest FFT event is the other parity's (recorded during the last call for the call
+    // before it).  Waiting on an event that was never recorded is a no-op.
+    for (int i = 0; i < 2; ++i) {
+        FRA_TRY(ctx, cudaStreamWaitEvent(st, ctx->pipe_k1_done[i], 0));
+        FRA_TRY(ctx, cudaStreamWaitEvent(st, ctx->pipe_k2_done[i], 0));
+    }
     return FRA_OK;
 }
 
@@ -831,10 +869,10 @@ int fra_process_host_async(fra_ctx *ctx, const int16_t *h_in, int continuous, in
                            const fra_outputs *h_out, uint64_t *ticket)
 {
     if (!ctx || !h_in || !h_out || !ticket) return FRA_ERR_INVALID;
-    FRA_TRY(ctx, pipe_host_join(ctx));
     if (log2_scale == FRA_SCALE_DEFAULT) log2_scale = -ctx->log2n;
     if (log2_scale < -40 || log2_scale > 16) return FRA_ERR_INVALID;
     FRA_TRY(ctx, cudaSetDevice(ctx->device));
+    FRA_TRY(ctx, pipe_host_join(ctx));                 // may launch the held-back FFT: after the device is current
     const size_t C = (size_t)ctx->channels, n = (size_t)ctx->n;
     auto need = [&](void **p, size_t bytes) -> bool { return *p || cudaMalloc(p, bytes) == cudaSuccess; };
     if (!need((void **)&ctx->d_in, C * n * 2)) return FRA_ERR_NOMEM;
@@ -947,7 +985,10 @@ int fra_iir_stream(fra_ctx *ctx, const int16_t *d_in, int16_t *d_out, size_t n, 
                                          : std::max(std::fabs((-a1 + std::sqrt(disc)) / 2.0), std::fabs((-a1 - std::sqrt(disc)) / 2.0));
             r = std::max(r, rs);
         }
-        if (r >= 0.9995) exact = 1;                       // (A^L) does not decay: use the exact chain
+        if (r >= 0.9995) {                                // (A^L) does not decay: use the exact chain
+            if ((n % kSplitChunk) != 0) return FRA_ERR_UNSUPPORTED;
+            exact = 1;
+        }
     }
 
     ctx->last_kernels = 0;
@@ -966,7 +1007,7 @@ int fra_iir_stream(fra_ctx *ctx, const int16_t *d_in, int16_t *d_out, size_t n, 
         k1.speculate = (ctx->flags & FRA_K1_SPECULATE) ? 1 : 0;
         const size_t smem = (size_t)kSplitWarps * kSplitSmemPerWarp;
         auto kfn = k1_split;
-        FRA_TRY(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FRA_SMEM(ctx, kfn, (int)smem);
         FRA_LAUNCH(kfn, dim3(1), dim3(kSplitWarps * 32), smem, st, k1);
         FRA_TRY(ctx, cudaGetLastError());
         ctx->last_kernels++;
@@ -1107,9 +1148,15 @@ int fra_iir_stream(fra_ctx *ctx, const int16_t *d_in, int16_t *d_out, size_t n, 
     // the dead band of a truncating section grows like 1 / (1 - r^2) (measured: 6-7 LSB at r^2 = 0.84,
     // 65 LSB at r^2 = 0.984); far beyond it the trajectories have separated
     const int dead_band = std::max(kStreamMaxDeadband, (int)(6.0 / std::max(1e-3, 1.0 - r * r)));
-    if (iir && counts[1] > dead_band && (n % kSplitChunk) == 0) {
+    if (iir && counts[1] > dead_band) {
         // beyond the dead band: the cascade is overflowing (16-bit wrap) or barely
-        // stable, trajectories do not stay together - recompute exactly
+        // stable, trajectories do not stay together - recompute exactly.  The exact chain
+        // needs n % 256 == 0; otherwise the approximate output is NOT handed out as valid
+        // and channel 0's history is left as it was.
+        if ((n % kSplitChunk) != 0) {
+            if (stats) *stats = s;
+            return FRA_ERR_UNSUPPORTED;
+        }
         rc = run_exact();
     } else if (iir) {
         // the stream's end state becomes channel 0's history (continuous operation)

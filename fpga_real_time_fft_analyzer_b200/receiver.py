@@ -163,6 +163,10 @@ class GpuReceiver:
         self._first = False
         if hasattr(x, "is_cuda") and x.is_cuda:
             out = self.ctx.process(x, continuous=carry, want=self.want)
+            if self.ctx.flags & _abi.FRA_PIPELINE:
+                # a pipelined context holds this call's FFT back until the next call: a receiver hands
+                # its frames out now, so the current stream joins the internal streams first
+                self.ctx.join()
         else:
             out = self.ctx.process_host(x, continuous=carry, want=self.want)
         self.stats["batches"] += 1

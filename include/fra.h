@@ -146,9 +146,12 @@ int fra_process(fra_ctx *ctx, const int16_t *d_in, int continuous, int log2_scal
  * average across calls and must be the same (initially zeroed or primed) buffer every call. */
 int fra_set_mag_average(fra_ctx *ctx, float alpha);
 
-/* The same step through host buffers: pinned staging + H2D, fra_process, D2H of
- * the requested outputs, synchronised on return.  This is the call a GpuReceiver
- * backend makes per batch of frames; h_out fields are HOST pointers. */
+/* The same step through host buffers: H2D of h_in, fra_process, D2H of the requested
+ * outputs, synchronised on return.  The copies are cudaMemcpyAsync straight from / into the
+ * caller's buffers (no staging copy inside the library): page-locked buffers (cudaHostAlloc,
+ * cudaHostRegister, torch pin_memory) overlap with the kernels; pageable ones still work but
+ * every copy then blocks the calling thread.  This is the call a GpuReceiver backend makes
+ * per batch of frames; h_out fields are HOST pointers. */
 int fra_process_host(fra_ctx *ctx, const int16_t *h_in, int continuous, int log2_scale,
                      const fra_outputs *h_out);
 
@@ -184,7 +187,10 @@ int fra_set_state(fra_ctx *ctx, const int16_t *d_state, void *cuda_stream);
  *               sections, a few LSB from the serial result; `stats` reports how many
  *               chunk boundaries differ and by how many LSB.  n multiple of 8.  Falls
  *               back to the exact path when the poles are too close to the unit circle
- *               or the deviation shows an overflowing (wrapping) cascade (stats->exact).
+ *               or the deviation shows an overflowing (wrapping) cascade (stats->exact);
+ *               that fallback needs n % 256 == 0 like the exact path itself - otherwise
+ *               the call returns FRA_ERR_UNSUPPORTED, d_out is not valid and the history
+ *               is left untouched.
  * Synchronous. */
 typedef struct fra_stream_stats {
     int exact;          /* 1 if the exact path produced the output */

@@ -305,14 +305,20 @@ def float_sos(coeff12) -> np.ndarray:
     return np.asarray(sos, dtype=np.float64)
 
 
-def cpu_float_chain(x: np.ndarray, coeff12, rom: np.ndarray):
+def cpu_float_chain(x: np.ndarray, coeff12, rom: np.ndarray, zi=None):
     """The 'repo's CPU path' of BASELINE.md section 3: numpy window, scipy sosfilt,
-    np.fft.fft, abs.  float64.  Used only as the timed CPU baseline."""
+    np.fft.fft, abs.  float64.  Used only as the timed CPU baseline.
+    zi (sosfilt's [sections, channels, 2] delay values): the filter history carried from the
+    previous frame (BASELINE config 3, continuous channels); the new one is returned third."""
     from scipy.signal import sosfilt
     xf = x.astype(np.float64) * (rom.astype(np.float64) / 32768.0)
-    yf = sosfilt(float_sos(coeff12), xf, axis=-1)
+    if zi is None:
+        yf = sosfilt(float_sos(coeff12), xf, axis=-1)
+        bins = np.fft.fft(yf, axis=-1)
+        return bins, np.abs(bins)
+    yf, zf = sosfilt(float_sos(coeff12), xf, axis=-1, zi=zi)
     bins = np.fft.fft(yf, axis=-1)
-    return bins, np.abs(bins)
+    return bins, np.abs(bins), zf
 
 
 # ------------------------------------------------------------------- stimulus

@@ -222,6 +222,104 @@ def test_config3_continuous_sharded_channels(fra, rom):
         assert np.array_equal(ctx.get_state()[pick].cpu().numpy(), st)
 
 
+@pytest.mark.parametrize("channels,frames", [(65536, 8), (32768, 3), (16384, 3), (8192, 3)])
+def test_config3_default_dispatch_continuous(fra, rom, channels, frames):
+    """BASELINE config 3 on the kernel the product picks by itself (no FORCE_* flag): 65536
+    continuous channels over 8 frames (the one-GPU case), and the shares of 2, 4 and 8 GPUs
+    (32768 = the window where the lane-per-channel kernel is chosen).  A seeded subset of the
+    channels against the golden model run over the concatenated stream, final history equal,
+    and the last frame's bins = floor(FFT(filtered) / N) within 1 LSB."""
+    c, n = channels, 16384
+    rng = np.random.default_rng(c)
+    pick = np.unique(np.concatenate([[0, 1, 31, 32, c // 2 - 1, c // 2, c - 33, c - 32, c - 1], rng.integers(0, c, 40)]))
+    pick_t = torch.from_numpy(pick).cuda()
+    with fra.FraContext(c, n) as ctx:
+        ctx.command(0x00)
+        out = {"filtered": torch.empty((c, n), dtype=torch.int16, device="cuda"),
+               "frames": torch.empty((c, 4 * n), dtype=torch.uint8, device="cuda")}
+        st = None
+        for f in range(frames):
+            x = fra.synth.tone_noise(c, n, "cuda", frame=f)
+            if f == 1:
+                x[pick_t[:8]] = fra.synth.full_range(8, n, "cuda", seed=f)      # full-range int16 on a few of them
+            ctx.process(x, continuous=f > 0, want=("filtered", "frames"), out=out)
+            assert ctx.last_kernel_count == 2
+            y, st = cg.window_iir(x[pick_t].cpu().numpy(), rom, 0, g.BANK0_COEFF, B1, st)
+            assert np.array_equal(out["filtered"][pick_t].cpu().numpy(), y), f
+            del x
+        assert np.array_equal(ctx.get_state()[pick_t].cpu().numpy(), st)
+        re, im, _ = g.decode_frame(out["frames"][pick_t].cpu().numpy())
+        rq, iq_ = g.quantize_bins(np.fft.fft(y.astype(np.float64), axis=-1), -14)
+        assert np.abs(re - rq).max() <= 1 and np.abs(im - iq_).max() <= 1
+        # every channel: the int16 frame is Hermitian (X[N-k] = conj(X[k]) up to the floor of -im)
+        fr = out["frames"].view(torch.int16).view(c, n, 2)
+        assert torch.equal(fr[:, 1:, 0], fr[:, 1:, 0].flip(1))
+
+
+def test_pipeline_mode_config2_size(fra, rom):
+    """FRA_PIPELINE at the 4096-channel configuration (one window+IIR CTA per SM beside two FFT
+    CTAs - the co-residency the mode exists for): same bytes as the sequential context."""
+    c, n, frames = 4096, 16384, 4
+    xs = [fra.synth.tone_noise(c, n, "cuda", frame=f) for f in range(frames)]
+    xs[2][:64] = fra.synth.full_range(64, n, "cuda", seed=3)
+    want = []
+    with fra.FraContext(c, n) as ref:
+        ref.command(0x00)
+        for i, x in enumerate(xs):
+            want.append(ref.process(x, continuous=i > 0, want=("frames",))["frames"].clone())
+        st_ref = ref.get_state().clone()
+    with fra.FraContext(c, n, flags=fra._abi.FRA_PIPELINE) as ctx:
+        ctx.command(0x00)
+        got = [ctx.process(x, continuous=i > 0, want=("frames",))["frames"] for i, x in enumerate(xs)]
+        ctx.join()
+        torch.cuda.synchronize()
+        for i in range(frames):
+            assert torch.equal(got[i], want[i]), i
+        assert torch.equal(ctx.get_state(), st_ref)
+    pick = np.array([0, 63, 64, 2047, 4095])
+    y, st = None, None
+    for x in xs:
+        y, st = cg.window_iir(x[pick].cpu().numpy(), rom, 0, g.BANK0_COEFF, B1, st)
+    assert np.array_equal(st_ref[pick].cpu().numpy(), st)
+
+
+def test_command_bytes_inside_an_upload_are_data(fra, rom):
+    """rx_filter_coeff's busy masking (NEW/command_control.vhd:51) on the real library: payload
+    bytes that look like commands (0xFF, 0x00, 0xF1, 0xB1) are coefficients, arbitrary
+    fragmentation of the byte stream, and the filter then runs with exactly those bytes."""
+    n, c = 2048, 40
+    rng = np.random.default_rng(77)
+    payload = np.array([0xFF, 0x00, 0xF1, 0xB1, 0x15, 0x00, 0xA1, 0x55, 0xA5, 0xEF, 0xFE, 0xFF], dtype=np.uint8)
+    stream = bytes([0x00, 0xF1]) + payload.tobytes() + bytes([0xA1, 0x42])
+    with fra.FraContext(c, n) as ctx:
+        dec = g.CommandDecoder()
+        pos = 0
+        while pos < len(stream):
+            k = int(rng.integers(1, 5))
+            done = ctx.command(stream[pos:pos + k])
+            dec.feed(stream[pos:pos + k])
+            assert done == (not dec.busy)
+            pos += k
+        assert ctx.mode == dec.mode == 0xA1
+        assert np.array_equal(ctx.bank(1), payload.view(np.int8)) and np.array_equal(dec.bank1, payload.view(np.int8))
+        assert ctx.counters() == {"start": 0, "request": 0, "reset": 0, "upload": 1}
+        x = adversarial(rng, c, n)
+        y, _ = cg.window_iir(x, rom, 0xA1, g.BANK0_COEFF, payload.view(np.int8))
+        assert np.array_equal(ctx.process(dev(x), want=("filtered",))["filtered"].cpu().numpy(), y)
+        # random streams: the library's decoder state equals the oracle decoder's
+        interesting = [0x00, 0xA1, 0xB1, 0x55, 0xA5, 0xEF, 0xFE, 0xF1, 0x42]
+        for trial in range(10):
+            s2 = bytes(int(rng.choice(interesting)) if rng.random() < 0.7 else int(rng.integers(0, 255))
+                       for _ in range(int(rng.integers(1, 80))))
+            ctx.command(s2)
+            dec.feed(s2)
+            assert ctx.mode == dec.mode and ctx.transport == dec.transport
+            assert np.array_equal(ctx.bank(1), dec.bank1)
+            while dec.busy:                               # finish the upload so that the next trial starts idle
+                ctx.command(b"\x01")
+                dec.feed(b"\x01")
+
+
 def test_config4_dual_banks_reload_and_all_outputs(fra, rom):
     """BASELINE config 4: bytes A1, then F1 + 12 at a frame boundary mid-run, then 00;
     int16 I/Q frame + fp32 magnitude + fp32 phase."""

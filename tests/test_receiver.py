@@ -56,3 +56,31 @@ def test_gpu_receiver_protocol_and_frames(rom, gui_vectors):
     finally:
         rx.stop()
     assert not rx.active and rx.send_command(0x00) is False
+
+
+@pytest.mark.gpu
+def test_gpu_receiver_on_a_pipelined_context(rom):
+    """A FRA_PIPELINE context holds the FFT of a call back until the next one; the receiver joins
+    before it hands frames out, so poll() returns finished frames (not uninitialised memory) for
+    CUDA sources too."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("needs a CUDA device; there is no CPU fallback")
+    from fpga_real_time_fft_analyzer_b200 import GpuReceiver, _abi
+    c, n = 6, 16384
+    batches = [g.tone_noise(range(c), n=n, seed=s) for s in range(3)]
+    it = iter(torch.from_numpy(b).cuda() for b in batches)
+    ref = GpuReceiver(lambda: None, channels=c, fft_size=n)
+    rx = GpuReceiver(lambda: next(it), channels=c, fft_size=n, flags=_abi.FRA_PIPELINE)
+    try:
+        for r in (ref, rx):
+            assert r.send_command(0x00) and r.send_ethernet_start()
+        for b in batches:
+            got = rx.poll()
+            want = ref.process_batch(torch.from_numpy(b).cuda())["frames"].cpu().numpy()
+            assert len(got) == c
+            for ch in range(c):
+                assert got[ch] == want[ch].tobytes()
+    finally:
+        rx.stop()
+        ref.stop()
