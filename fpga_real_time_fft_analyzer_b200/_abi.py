@@ -34,6 +34,7 @@ FRA_K1_SPECULATE = 0x8
 FRA_K1_FORCE_STAGE = 0x10
 FRA_K1_FORCE_DUO = 0x20
 FRA_PIPELINE = 0x40
+FRA_K1_NO_BIASED = 0x80
 
 
 class FraOutputs(C.Structure):

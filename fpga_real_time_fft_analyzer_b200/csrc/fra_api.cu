@@ -63,6 +63,7 @@ struct fra_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_streams[3] = {nullptr, nullptr, nullptr};
     int *d_rom32 = nullptr;
+    int *d_rom2x = nullptr;           // 2 * ROM: the window straight to the biased float (window_biased)
     int16_t *d_state = nullptr;       // [C][6][4]
     int16_t *d_scratch = nullptr;     // [C][N] filter output when the caller does not ask for it
     float2 *d_tw1 = nullptr, *d_tw2 = nullptr, *d_twn = nullptr;
@@ -148,6 +149,7 @@ StageCoef make_stage(const int8_t *k)       // k = B0,B1,B2,A0,A1 (NEW/filter_ii
     c.na1 = -(float)k[4] / 128.0f;
     c.exp23 = 0x4B000000u;
     c.k0 = kMagicB + (float)k[4] * 65792.0f;
+    c.kb = (float)(12615680 - 65792 * ((int)k[0] + (int)k[1] + (int)k[2] - (int)k[3] - (int)k[4]));   // exact: a multiple of 256 below 2^26
     return c;
 }
 
@@ -339,6 +341,7 @@ int process_range(fra_ctx *ctx, const int16_t *d_in, int c0, int nch, int contin
         k1.out = filt;
         k1.state = ctx->d_state + (size_t)c0 * 24;
         k1.rom32 = ctx->d_rom32;
+        k1.rom2x = ctx->d_rom2x;
         const Sections sec = current_sections(ctx);
         k1.coef = make_cascade(sec);
         k1.channels = nch;
@@ -356,19 +359,23 @@ int process_range(fra_ctx *ctx, const int16_t *d_in, int c0, int nch, int contin
         if (ctx->flags & FRA_K1_FORCE_SPLIT) variant = 1;
         if (ctx->flags & FRA_K1_FORCE_STAGE) variant = 2;
         if (ctx->flags & FRA_K1_FORCE_DUO) variant = 3;
-        bool b1z = true, fast = true;
+        bool b1z = true, fast = true, biased = !(ctx->flags & FRA_K1_NO_BIASED);
         for (int i = 0; i < kStages; ++i) {
             b1z = b1z && sec.c[i][1] == 0;                       // x[n-1] coefficient zero in every stage: skip that product
             fast = fast && std::abs((int)sec.c[i][4]) <= kFastMaxA1;   // two-instruction recurrence (fra_common.cuh)
+            // every operand biased, no FADD at all (fra_common.cuh: biquad_step_biased)
+            biased = biased && biased_order_ok(sec.c[i][0], sec.c[i][1], sec.c[i][2], sec.c[i][3], sec.c[i][4]);
         }
         if (variant == 3) {
             const int grid = (nch + 31) / 32;
             bool alt = true;                                       // ALPHA, BETA, ALPHA, BETA, ALPHA, BETA
             for (int i = 2; i < kStages; ++i) alt = alt && std::memcmp(sec.c[i], sec.c[i & 1], 5) == 0;
-            void (*const table[8])(K1Args) = {
-                k1_duo<false, false, false>, k1_duo<true, false, false>, k1_duo<false, true, false>, k1_duo<true, true, false>,
-                k1_duo<false, false, true>,  k1_duo<true, false, true>,  k1_duo<false, true, true>,  k1_duo<true, true, true>};
-            auto kfn = table[(b1z ? 1 : 0) | (fast ? 2 : 0) | (alt ? 4 : 0)];
+            void (*const table[12])(K1Args) = {
+                k1_duo<false, 0, false>, k1_duo<true, 0, false>, k1_duo<false, 1, false>, k1_duo<true, 1, false>,
+                k1_duo<false, 2, false>, k1_duo<true, 2, false>,
+                k1_duo<false, 0, true>,  k1_duo<true, 0, true>,  k1_duo<false, 1, true>,  k1_duo<true, 1, true>,
+                k1_duo<false, 2, true>,  k1_duo<true, 2, true>};
+            auto kfn = table[(b1z ? 1 : 0) + 2 * (biased ? 2 : fast ? 1 : 0) + (alt ? 6 : 0)];
             static_assert(kDuoSmemRequest >= kDuoSmemBytes, "k1_duo shared memory");
             FRA_SMEM(ctx, kfn, kDuoSmemRequest);
             FRA_LAUNCH(kfn, dim3(grid), dim3(kDuoWarps * 32), (size_t)kDuoSmemRequest, st, k1);
@@ -386,7 +393,7 @@ int process_range(fra_ctx *ctx, const int16_t *d_in, int c0, int nch, int contin
             FRA_LAUNCH(kfn, dim3(grid), dim3(kSplitWarps * 32), smem, st, k1);
         } else {
             const int grid = (nch + kLaneBlock - 1) / kLaneBlock;
-            auto kfn = b1z ? k1_lane<true> : k1_lane<false>;
+            auto kfn = biased ? (b1z ? k1_lane_biased<true> : k1_lane_biased<false>) : (b1z ? k1_lane<true> : k1_lane<false>);
             FRA_LAUNCH(kfn, dim3(grid), dim3(kLaneBlock), (size_t)0, st, k1);
         }
         FRA_TRY(ctx, cudaGetLastError());
@@ -555,6 +562,7 @@ int fra_create(fra_ctx **out, int device, int n_channels, int fft_size, unsigned
 
     const size_t n = (size_t)fft_size;
     if (cudaMalloc((void **)&ctx->d_rom32, kWindowLen * sizeof(int)) != cudaSuccess) return bail(FRA_ERR_NOMEM);
+    if (cudaMalloc((void **)&ctx->d_rom2x, kWindowLen * sizeof(int)) != cudaSuccess) return bail(FRA_ERR_NOMEM);
     if (cudaMalloc((void **)&ctx->d_state, (size_t)n_channels * 24 * sizeof(int16_t)) != cudaSuccess) return bail(FRA_ERR_NOMEM);
     if (cudaMalloc((void **)&ctx->d_tw1, 256 * sizeof(float2)) != cudaSuccess) return bail(FRA_ERR_NOMEM);
     if (cudaMalloc((void **)&ctx->d_tw2, 4096 * sizeof(float2)) != cudaSuccess) return bail(FRA_ERR_NOMEM);
@@ -562,8 +570,11 @@ int fra_create(fra_ctx **out, int device, int n_channels, int fft_size, unsigned
     const size_t n_kernel = std::min<size_t>(n, (size_t)kHalf64k);
     if (cudaMalloc((void **)&ctx->d_twn, (n_kernel / 2) * sizeof(float2)) != cudaSuccess) return bail(FRA_ERR_NOMEM);
 
-    std::vector<int> rom32(kWindowLen);
-    for (int i = 0; i < kWindowLen; ++i) rom32[i] = kHannRom[i];
+    std::vector<int> rom32(kWindowLen), rom2x(kWindowLen);
+    for (int i = 0; i < kWindowLen; ++i) {
+        rom32[i] = kHannRom[i];
+        rom2x[i] = 2 * kHannRom[i];
+    }
     std::vector<float2> tw1(256), tw2(4096), twn(n_kernel / 2);
     const double two_pi = 6.283185307179586476925286766559;
     for (int r = 0; r < 16; ++r)
@@ -591,6 +602,7 @@ int fra_create(fra_ctx **out, int device, int n_channels, int fft_size, unsigned
             return bail(FRA_ERR_CUDA);
     }
     if (cudaMemcpy(ctx->d_rom32, rom32.data(), rom32.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(ctx->d_rom2x, rom2x.data(), rom2x.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(ctx->d_tw1, tw1.data(), tw1.size() * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(ctx->d_tw2, tw2.data(), tw2.size() * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(ctx->d_twn, twn.data(), twn.size() * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess ||
@@ -627,7 +639,7 @@ int fra_destroy(fra_ctx *ctx)
         if (ps) { cudaStreamSynchronize(ps); cudaStreamDestroy(ps); }
     for (cudaEvent_t pe : {ctx->pipe_in, ctx->pipe_go, ctx->pipe_k1_done[0], ctx->pipe_k1_done[1], ctx->pipe_k2_done[0], ctx->pipe_k2_done[1]})
         if (pe) cudaEventDestroy(pe);
-    void *bufs[] = {ctx->d_rom32, ctx->d_state, ctx->d_scratch, ctx->d_tw1, ctx->d_tw2, ctx->d_twn, ctx->d_in, ctx->d_twc, ctx->d_halves, ctx->d_split,
+    void *bufs[] = {ctx->d_rom32, ctx->d_rom2x, ctx->d_state, ctx->d_scratch, ctx->d_tw1, ctx->d_tw2, ctx->d_twn, ctx->d_in, ctx->d_twc, ctx->d_halves, ctx->d_split,
                     ctx->d_frames, ctx->d_filtered_out, ctx->d_iq, ctx->d_mag, ctx->d_phase, ctx->d_entry,
                     ctx->d_exit, ctx->d_counts, ctx->d_ends, ctx->d_aggr, ctx->d_mats};
     for (void *p : bufs)
@@ -1000,6 +1012,7 @@ int fra_iir_stream(fra_ctx *ctx, const int16_t *d_in, int16_t *d_out, size_t n, 
         k1.out = d_out;
         k1.state = ctx->d_state;
         k1.rom32 = ctx->d_rom32;
+        k1.rom2x = ctx->d_rom2x;
         k1.coef = make_cascade(sec);
         k1.channels = 1;
         k1.n = (int)n;

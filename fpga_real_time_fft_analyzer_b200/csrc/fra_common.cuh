@@ -62,6 +62,7 @@ struct StageCoef {
     unsigned exp23;      // 0x4B000000, passed as data so that it lives in a register and
                          // PRMT's selector can be the immediate (one instruction, no re-materialised selector)
     float k0;            // kMagicB + A1 * 65792: accumulator start for biquad_step_fast
+    float kb;            // kMagicB - 65792 (B0 + B1 + B2 - A0 - A1): accumulator start for biquad_step_biased
 };
 
 // biquad_step_fast is usable when kMagicB + A1 * 65792 +- (the partial sums, < 2^17.4) stays
@@ -136,6 +137,56 @@ FRA_DEV float biquad_step_fast(float x, const StageCoef &k, StageState &s, float
     return acc;
 }
 
+// The all-biased step: EVERY operand - x[n], x[n-1], x[n-2], y[n-1], y[n-2] - is the PRMT output
+// u = v + kBias16 of the stage (or window) that produced it, so no FADD removes a bias anywhere:
+// five FFMAs and one PRMT per stage and sample.  An FFMA forms u * (c/128) + acc exactly before
+// its single rounding, and u * (c/128) = v * c/128 + 65792 c with 65792 c an integer, so each
+// biased operand shifts the accumulator by a known integer.  The accumulator starts at
+// kb = kMagicB - 65792 (B0 + B1 + B2 - A0 - A1); after the k-th product it holds
+//   kMagicB + (true partial sum) - 65792 * (signed coefficients of the products still to come)
+// and the rounding of every FFMA gives the same integer as in biquad_step as long as that value
+// stays inside [2^23, 2^24): the coefficient sum of every SUFFIX of the product order
+// (y[n-2], x[n-2], x[n-1], x[n], y[n-1]) must lie within +-kBiasedMaxSuffix.  The start value may be
+// anywhere (it is an exact constant; only results are rounded), which is why the large y[n-2]
+// coefficient of the reference's fixed bank (A0 = 107) goes first.  biased_order_ok() is the
+// host-side test; coefficient sets that fail it use biquad_step / biquad_step_fast.
+// tests/host/check_q15_math.cpp proves the identity for every int16 x int8 at the extreme
+// accumulator values the condition allows.
+constexpr int kBiasedMaxSuffix = 60;
+
+inline bool biased_order_ok(int b0, int b1, int b2, int a0, int a1)
+{
+    const int term[5] = {-a0, b0, b1, b2, -a1};          // product order of biquad_step_biased
+    int suffix = 0;
+    for (int k = 4; k >= 1; --k) {
+        suffix += term[k];
+        if (suffix > kBiasedMaxSuffix || suffix < -kBiasedMaxSuffix) return false;
+    }
+    return true;
+}
+
+typedef StageState StageStateB;     // the same four registers, each biased by kBias16 (bit pattern 0x4B00xxxx)
+
+// int in [-32768, 32767] -> v + kBias16 with one integer add (0x4B008000 = bits of kBias16)
+FRA_DEV float biased_from_int(int v) { return __uint_as_float((unsigned)v + 0x4B008000u); }
+// biased float -> its int16 as the low 16 bits (two's complement)
+FRA_DEV unsigned biased_to_u16(float u) { return (__float_as_uint(u) ^ 0x8000u) & 0xFFFFu; }
+
+template <bool B1Z = false>
+FRA_DEV float biquad_step_biased(float ux, const StageCoef &k, StageStateB &s, float *u_out)
+{
+    float acc = __fmaf_ru(s.y2, k.na0, k.kb);
+    acc = __fmaf_rd(s.x2, k.b0, acc);
+    if (!B1Z) acc = __fmaf_rd(s.x1, k.b1, acc);
+    acc = __fmaf_rd(ux, k.b2, acc);                 // x arrives late (previous stage): fourth
+    acc = __fmaf_ru(s.y1, k.na1, acc);              // y[n-1] is the recurrence: last
+    const float u = __uint_as_float(__byte_perm(__float_as_uint(acc), k.exp23, 0x7610));
+    s.x2 = s.x1; s.x1 = ux;
+    s.y2 = s.y1; s.y1 = u;
+    *u_out = u;
+    return acc;
+}
+
 // Speculative form of the same step for the latency-bound systolic kernel: assume the
 // five-term sum does not leave the int16 range (true unless the filter overflows), so
 // y = acc - kMagicB exactly and the recurrence is FFMA -> FADD instead of
@@ -167,6 +218,18 @@ FRA_DEV int window_int(int x, int c)
 
 // the same without the resize quirk: valid whenever c != -32768 (all but 30 ROM entries)
 FRA_DEV int window_int_fast(int x, int c) { return (x * c + 16384) >> 15; }
+
+// The window straight to the biased float of biquad_step_biased, two instructions: with c2 = 2 c
+// (a second ROM table), (x c + 2^14) >> 15 = (x c2 + 2^15) >> 16, i.e. the HIGH half of
+// p = x c2 + 0x8000; adding 0x80000000 as well turns that half into offset-binary, and one PRMT
+// splices it under the exponent of 2^23: 2^23 + 2^15 + window(x, c).  One IMAD (the constant
+// 0x80008000 is its addend) and one PRMT.  Valid whenever c != -32768 (x c2 then fits 32 bits and the
+// result fits int16); the 30 ROM entries equal to -32768 take window_int + biased_from_int.
+FRA_DEV float window_biased(int x, int c2, unsigned exp23)
+{
+    const unsigned p = (unsigned)(x * c2) + 0x80008000u;
+    return __uint_as_float(__byte_perm(p, exp23, 0x7632));
+}
 
 // int in [-32768, 32767] -> float without the conversion pipe
 FRA_DEV float small_int_to_float(int v)

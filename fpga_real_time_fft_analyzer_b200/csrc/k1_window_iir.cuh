@@ -29,6 +29,7 @@ struct K1Args {
     int16_t *out;           // [C][N]
     int16_t *state;         // [C][6][4], read when continuous, always written
     const int *rom32;       // [16384] window ROM widened to int32
+    const int *rom2x;       // [16384] 2 * ROM (window_biased)
     CascadeCoef coef;
     int channels;
     int n;                  // samples per frame, multiple of 256
@@ -120,6 +121,123 @@ __global__ void __launch_bounds__(kLaneBlock) k1_lane(K1Args a)
             v.y = pack16((unsigned)(int)st[s].y1, (unsigned)(int)st[s].y2);
             sp[s] = v;
         }
+    }
+}
+
+// ------------------------------------------------------------- k1_lane_biased
+// The lane-per-channel kernel on the all-biased step (fra_common.cuh: biquad_step_biased): every
+// value that moves between the window, the six stages and the history registers is the PRMT
+// output v + kBias16, so a stage is five FFMAs (four when the x[n-1] coefficient is zero) and one
+// PRMT, the window is IMAD + PRMT, and nothing on the path converts or removes a bias.
+// ~35 issue slots per sample with the reference's fixed bank.
+FRA_DEV float biased_from_i16(unsigned half_word_lo16)      // int16 in the low half of a word -> v + kBias16
+{
+    return __uint_as_float(((half_word_lo16 ^ 0x8000u) & 0xFFFFu) | 0x4B000000u);
+}
+
+FRA_DEV StageStateB load_state_biased(const int16_t *state, size_t c, int s, bool continuous)
+{
+    const uint2 v = continuous ? __ldg(reinterpret_cast<const uint2 *>(state + (c * kStages + s) * 4)) : make_uint2(0u, 0u);
+    StageStateB st;
+    st.x1 = biased_from_i16(v.x);
+    st.x2 = biased_from_i16(v.x >> 16);
+    st.y1 = biased_from_i16(v.y);
+    st.y2 = biased_from_i16(v.y >> 16);
+    return st;
+}
+
+FRA_DEV void store_state_biased(int16_t *state, size_t c, int s, const StageStateB &st)
+{
+    uint2 v;
+    v.x = pack16(__float_as_uint(st.x1), __float_as_uint(st.x2)) ^ 0x80008000u;
+    v.y = pack16(__float_as_uint(st.y1), __float_as_uint(st.y2)) ^ 0x80008000u;
+    *reinterpret_cast<uint2 *>(state + (c * kStages + s) * 4) = v;
+}
+
+// window + bias for 8 packed samples whose 8 doubled ROM entries are ra, rb; QUIRK: the entries may
+// be -32768 (2c = -65536), where the product overflows and the result needs the resize fix-up
+template <bool QUIRK>
+FRA_DEV void window8_biased(uint4 x, int4 ra, int4 rb, unsigned exp23, float (&u)[8])
+{
+    auto w = [&](int v, int c2) {
+        return QUIRK ? biased_from_int(window_int(v, c2 >> 1)) : window_biased(v, c2, exp23);
+    };
+    u[0] = w(lo16(x.x), ra.x); u[1] = w(hi16(x.x), ra.y); u[2] = w(lo16(x.y), ra.z); u[3] = w(hi16(x.y), ra.w);
+    u[4] = w(lo16(x.z), rb.x); u[5] = w(hi16(x.z), rb.y); u[6] = w(lo16(x.w), rb.z); u[7] = w(hi16(x.w), rb.w);
+}
+
+// ROM entries equal to -32768 live in [0, 15), [8178, 8206) and [16369, 16384): does [w0, w0 + len) touch one?
+FRA_DEV bool rom_quirk_range(int w0, int len)
+{
+    return (w0 < 15) || (w0 + len > 8178 && w0 < 8206) || (w0 + len > 16369);
+}
+
+template <bool B1Z>
+__global__ void __launch_bounds__(kLaneBlock) k1_lane_biased(K1Args a)
+{
+    const int c_raw = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = c_raw < a.channels;
+    const int c = live ? c_raw : a.channels - 1;     // inactive lanes shadow the last channel (no stores)
+    const unsigned exp23 = a.coef.set[0].exp23;
+
+    StageStateB st[kStages];
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) st[s] = load_state_biased(a.state, (size_t)c, s, a.continuous != 0);
+
+    const int16_t *src = a.in + (size_t)c * a.n;
+    int16_t *dst = a.out + (size_t)c * a.n;
+
+    __shared__ uint4 stage_x[2][2][kLaneBlock];      // [buffer][half][lane]: 16 samples per lane
+    __shared__ int4 stage_rom[2][4];                 // [buffer][4 x 4 doubled ROM entries]
+    const int lane = threadIdx.x;
+    auto request = [&](int n0, int b) {
+        cp_async16(&stage_x[b][0][lane], src + n0);
+        cp_async16(&stage_x[b][1][lane], src + n0 + 8);
+        if (lane < 4) cp_async16(&stage_rom[b][lane], a.rom2x + ((n0 + 4 * lane) & (kWindowLen - 1)));
+        cp_async_commit();
+    };
+    request(0, 0);
+    for (int n0 = 0, it = 0; n0 < a.n; n0 += 16, ++it) {
+        const int b = it & 1;
+        if (n0 + 16 < a.n) request(n0 + 16, b ^ 1);
+        else cp_async_commit();
+        cp_async_wait<1>();
+        __syncwarp();                                 // the ROM words were copied by lanes 0..3
+        const uint4 xa = stage_x[b][0][lane], xb = stage_x[b][1][lane];
+        const int4 r0 = stage_rom[b][0], r1 = stage_rom[b][1], r2 = stage_rom[b][2], r3 = stage_rom[b][3];
+        float u[16];
+        {
+            float ua[8], ub[8];
+            if (rom_quirk_range(n0 & (kWindowLen - 1), 16)) {      // warp-uniform
+                window8_biased<true>(xa, r0, r1, exp23, ua);
+                window8_biased<true>(xb, r2, r3, exp23, ub);
+            } else {
+                window8_biased<false>(xa, r0, r1, exp23, ua);
+                window8_biased<false>(xb, r2, r3, exp23, ub);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { u[j] = ua[j]; u[8 + j] = ub[j]; }
+        }
+        unsigned ow[8];
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+            float v0 = u[j], v1 = u[j + 1], acc0 = 0.0f, acc1 = 0.0f;
+#pragma unroll
+            for (int s = 0; s < kStages; ++s) acc0 = biquad_step_biased<B1Z>(v0, a.coef.set[s], st[s], &v0);
+#pragma unroll
+            for (int s = 0; s < kStages; ++s) acc1 = biquad_step_biased<B1Z>(v1, a.coef.set[s], st[s], &v1);
+            ow[j >> 1] = pack16_acc(acc0, acc1);
+        }
+        if (live) {
+            stg128(dst + n0, make_uint4(ow[0], ow[1], ow[2], ow[3]));
+            stg128(dst + n0 + 8, make_uint4(ow[4], ow[5], ow[6], ow[7]));
+        }
+        __syncwarp();                                 // everyone has read buffer b before it is refilled
+    }
+
+    if (live) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) store_state_biased(a.state, (size_t)c, s, st[s]);
     }
 }
 
@@ -478,7 +596,7 @@ FRA_DEV void stage_loader_step(const int16_t *src, const int *rom32, int t, int 
     const int4 *rom = reinterpret_cast<const int4 *>(srcq + 4 * 32);
     float4 *tile = stage_tile(smem, 0, t & 1) + (8 * half) * 32 + lane;
     const int w0 = (t * kStageChunk + 32 * half) & (kWindowLen - 1);
-    // ROM entries equal to -32768 live in [0, 15), [8178, 8206) and at 16383
+    // ROM entries equal to -32768 live in [0, 15), [8178, 8206) and [16369, 16384)
     const bool quirk = (w0 < 32) || (w0 >= 8160 && w0 < 8224) || (w0 >= kWindowLen - 32);
     if (quirk) stage_load_half<true>(cur, rom, tile);
     else stage_load_half<false>(cur, rom, tile);
@@ -630,16 +748,18 @@ FRA_DEV int duo_swz(int row, int piece) { return row * 128 + ((piece ^ (row & 7)
 // `last` branch per group is a basic-block boundary that drains both dependency chains four
 // times per chunk (21.4 instead of 17.9 cycles per sample).
 // one stage of a pair: the exact step, or its two-instruction-recurrence form (u = y + kBias16)
-template <bool B1Z, bool FAST>
+// MODE 0: biquad_step, 1: biquad_step_fast, 2: biquad_step_biased (tiles and history hold v + kBias16)
+template <bool B1Z, int FAST>
 FRA_DEV float duo_step(float x, const StageCoef &k, StageState &s, float &u)
 {
     float y;
-    if (FAST) (void)biquad_step_fast<B1Z>(x, k, s, u, &y);
+    if (FAST == 2) (void)biquad_step_biased<B1Z>(x, k, s, &y);
+    else if (FAST == 1) (void)biquad_step_fast<B1Z>(x, k, s, u, &y);
     else (void)biquad_step<B1Z>(x, k, s, &y);
     return y;
 }
 
-template <bool B1Z, bool FAST>
+template <bool B1Z, int FAST>
 FRA_DEV void duo_group16(const float4 (&in)[4], const StageCoef &ka, const StageCoef &kb, StageState &sa,
                          StageState &sb, float &ua, float &ub, float4 *tout)
 {
@@ -656,7 +776,7 @@ FRA_DEV void duo_group16(const float4 (&in)[4], const StageCoef &ka, const Stage
 }
 
 // one chunk (64 samples) through a stage pair, straight-line like stage_chunk
-template <bool B1Z, bool FAST>
+template <bool B1Z, int FAST>
 FRA_DEV void duo_chunk(const float4 *tin, float4 *tout, const StageCoef &ka, const StageCoef &kb, StageState &sa,
                        StageState &sb, float &ua, float &ub)
 {
@@ -675,6 +795,7 @@ FRA_DEV void duo_chunk(const float4 *tin, float4 *tout, const StageCoef &ka, con
 
 // loader, input side: chunk t+1's lines are requested (cp.async, whole lines) before chunk t
 // is windowed and converted into the loader->pair-0 tile
+template <bool BIASED>
 FRA_DEV void duo_loader_request(const K1Args &a, int c0, int t, unsigned char *smem_raw, int lane)
 {
     unsigned char *dst = smem_raw + kDuoInOff + (t & 1) * kDuoLineTileBytes;
@@ -687,14 +808,14 @@ FRA_DEV void duo_loader_request(const K1Args &a, int c0, int t, unsigned char *s
     }
     if (lane < 16)
         cp_async16(smem_raw + kDuoRomOff + (t & 1) * kDuoRomBytes + 16 * lane,
-                   a.rom32 + (((t * kStageChunk) & (kWindowLen - 1)) + 4 * lane));
+                   (BIASED ? a.rom2x : a.rom32) + (((t * kStageChunk) & (kWindowLen - 1)) + 4 * lane));
 }
 
 // (all shared-memory loads of a batch are issued before the first store: the compiler cannot
 // move a load above a store to memory it cannot tell apart, and a load -> convert -> store
 // sequence per piece costs one full shared-memory latency each)
-template <bool QUIRK>
-FRA_DEV void duo_convert_chunk(const unsigned char *lines, const int4 *rom, float4 *tile, int lane)
+template <bool QUIRK, bool BIASED>
+FRA_DEV void duo_convert_chunk(const unsigned char *lines, const int4 *rom, float4 *tile, int lane, unsigned exp23)
 {
     uint4 x[8];
 #pragma unroll
@@ -708,7 +829,14 @@ FRA_DEV void duo_convert_chunk(const unsigned char *lines, const int4 *rom, floa
         for (int j = 0; j < 4; ++j) {
             const int q = 4 * h + j;
             float4 fa, fb;
-            stage_convert8<QUIRK>(x[q], r[2 * j], r[2 * j + 1], fa, fb);
+            if (BIASED) {
+                float u[8];
+                window8_biased<QUIRK>(x[q], r[2 * j], r[2 * j + 1], exp23, u);
+                fa = make_float4(u[0], u[1], u[2], u[3]);
+                fb = make_float4(u[4], u[5], u[6], u[7]);
+            } else {
+                stage_convert8<QUIRK>(x[q], r[2 * j], r[2 * j + 1], fa, fb);
+            }
             tile[(2 * q) * 32] = fa;
             tile[(2 * q + 1) * 32] = fb;
         }
@@ -719,12 +847,15 @@ FRA_DEV void duo_convert_chunk(const unsigned char *lines, const int4 *rom, floa
 // channel) -> global memory, whole lines (eight lanes per channel).  The lines are staged in
 // the first half of the float tile itself, once every lane has read its part of it: the last
 // pair will not write this parity again before the next barrier.
+template <bool BIASED>
 FRA_DEV void duo_store_chunk(const K1Args &a, int c0, int chunk, unsigned char *smem_raw, int lane)
 {
     float4 *tile_base = stage_tile(reinterpret_cast<float *>(smem_raw), kDuoPairs, chunk & 1);
     const float4 *tile = tile_base + lane;
     unsigned char *lines = reinterpret_cast<unsigned char *>(tile_base);
-    auto pk = [](float u, float v) {           // u + 1.5 * 2^23 holds u mod 2^16 in its low mantissa bits
+    auto pk = [](float u, float v) {
+        // biased: the low halves are the values in offset-binary; else u + 1.5 * 2^23 holds u mod 2^16 in its low mantissa bits
+        if (BIASED) return pack16(__float_as_uint(u), __float_as_uint(v)) ^ 0x80008000u;
         return pack16(__float_as_uint(u + kMagic), __float_as_uint(v + kMagic));
     };
     uint4 o[8];
@@ -756,10 +887,11 @@ FRA_DEV void duo_store_chunk(const K1Args &a, int c0, int chunk, unsigned char *
     }
 }
 
+template <bool BIASED>
 FRA_DEV void duo_loader_step(const K1Args &a, int c0, int t, int n_chunks, unsigned char *smem_raw, int lane)
 {
     if (t >= n_chunks) return;
-    if (t + 1 < n_chunks) duo_loader_request(a, c0, t + 1, smem_raw, lane);
+    if (t + 1 < n_chunks) duo_loader_request<BIASED>(a, c0, t + 1, smem_raw, lane);
     cp_async_commit();
     cp_async_wait<1>();                                        // everything but the group just committed: chunk t is here
     __syncwarp();                                              // each line was copied by eight different lanes
@@ -767,10 +899,11 @@ FRA_DEV void duo_loader_step(const K1Args &a, int c0, int t, int n_chunks, unsig
     const int4 *rom = reinterpret_cast<const int4 *>(smem_raw + kDuoRomOff + (t & 1) * kDuoRomBytes);
     float4 *tile = stage_tile(reinterpret_cast<float *>(smem_raw), 0, t & 1) + lane;
     const int w0 = (t * kStageChunk) & (kWindowLen - 1);
-    // ROM entries equal to -32768 live in [0, 15), [8178, 8206) and at 16383
+    // ROM entries equal to -32768 live in [0, 15), [8178, 8206) and [16369, 16384)
     const bool quirk = (w0 < 64) || (w0 >= 8128 && w0 < 8256) || (w0 >= kWindowLen - 64);
-    if (quirk) duo_convert_chunk<true>(lines, rom, tile, lane);
-    else duo_convert_chunk<false>(lines, rom, tile, lane);
+    const unsigned exp23 = a.coef.set[0].exp23;
+    if (quirk) duo_convert_chunk<true, BIASED>(lines, rom, tile, lane, exp23);
+    else duo_convert_chunk<false, BIASED>(lines, rom, tile, lane, exp23);
 }
 
 FRA_DEV StageState duo_load_state(const K1Args &a, int cc, int s)
@@ -797,7 +930,7 @@ FRA_DEV void duo_store_state(const K1Args &a, int c, int s, const StageState &st
 // ALT: the six stages use two alternating coefficient sets (the RTL's bank layout): the pair's
 // coefficients are then compile-time addresses and stay in uniform registers (a run-time set index
 // moves them to vector registers and costs 5 %)
-template <bool B1Z, bool FAST, bool ALT>
+template <bool B1Z, int FAST, bool ALT>
 __global__ void __launch_bounds__(kDuoWarps * 32, 2) k1_duo(K1Args a)
 {
     FRA_DYN_SMEM(smem_raw);
@@ -814,11 +947,12 @@ __global__ void __launch_bounds__(kDuoWarps * 32, 2) k1_duo(K1Args a)
     timeline_mark(0, a.tl_step);
 #endif
 
+    constexpr bool BIASED = (FAST == 2);
     if (warp == 0) {
-        duo_loader_request(a, c0, 0, smem_raw, lane);
+        duo_loader_request<BIASED>(a, c0, 0, smem_raw, lane);
         cp_async_commit();
         for (int t = 0; t < n_steps; ++t) {
-            duo_loader_step(a, c0, t, n_chunks, smem_raw, lane);
+            duo_loader_step<BIASED>(a, c0, t, n_chunks, smem_raw, lane);
             __syncthreads();
         }
 #ifdef FRA_TIMELINE
@@ -828,14 +962,21 @@ __global__ void __launch_bounds__(kDuoWarps * 32, 2) k1_duo(K1Args a)
         // shares the loader's scheduler: both are short, latency-bound instruction streams
         for (int t = 0; t < n_steps; ++t) {
             const int done = t - (kDuoPairs + 1);                // the chunk the last pair finished in the step before
-            if (done >= 0) duo_store_chunk(a, c0, done, smem_raw, lane);
+            if (done >= 0) duo_store_chunk<BIASED>(a, c0, done, smem_raw, lane);
             __syncthreads();
         }
     } else {
         const int p = warp - 1;                                  // stage pair: stages 2p and 2p+1
         const StageCoef ka = a.coef.set[ALT ? 0 : 2 * p], kb = a.coef.set[ALT ? 1 : 2 * p + 1];
-        StageState sa = duo_load_state(a, cc, 2 * p), sb = duo_load_state(a, cc, 2 * p + 1);
-        float ua = sa.y1 + kBias16, ub = sb.y1 + kBias16;
+        StageState sa, sb;
+        if (BIASED) {
+            sa = load_state_biased(a.state, (size_t)cc, 2 * p, a.continuous != 0);
+            sb = load_state_biased(a.state, (size_t)cc, 2 * p + 1, a.continuous != 0);
+        } else {
+            sa = duo_load_state(a, cc, 2 * p);
+            sb = duo_load_state(a, cc, 2 * p + 1);
+        }
+        float ua = sa.y1 + kBias16, ub = sb.y1 + kBias16;        // biquad_step_fast only
         for (int t = 0; t < n_steps; ++t) {
             const int chunk = t - 1 - p;
             if (chunk >= 0 && chunk < n_chunks) {
@@ -845,8 +986,13 @@ __global__ void __launch_bounds__(kDuoWarps * 32, 2) k1_duo(K1Args a)
             __syncthreads();
         }
         if (live) {
-            duo_store_state(a, c, 2 * p, sa);
-            duo_store_state(a, c, 2 * p + 1, sb);
+            if (BIASED) {
+                store_state_biased(a.state, (size_t)c, 2 * p, sa);
+                store_state_biased(a.state, (size_t)c, 2 * p + 1, sb);
+            } else {
+                duo_store_state(a, c, 2 * p, sa);
+                duo_store_state(a, c, 2 * p + 1, sb);
+            }
         }
     }
 }

@@ -73,6 +73,9 @@ typedef enum fra_status {
 #define FRA_K1_SPECULATE    0x8u     /* systolic kernel: try the no-overflow recurrence (FFMA->FADD) first and roll a block
                                         back when a sum left the int16 range; same results, measured no faster on B200 */
 
+#define FRA_K1_NO_BIASED    0x80u    /* never use the all-biased biquad step (five FFMAs + one PRMT per stage);
+                                        same results - for A/B timing and to test the general step with eligible coefficients */
+
 typedef struct fra_ctx fra_ctx;      /* opaque: ROM, two coefficient banks, IIR state, twiddles, one stream */
 
 /* Lifetime.  n_channels independent channels, fft_size in {1024,...,65536}

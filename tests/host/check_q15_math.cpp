@@ -73,6 +73,47 @@ int main()
             }
         }
     }
+    // 7. biquad_step_biased: every operand biased by kBias16.  For every int8 coefficient and every
+    //    int16 v, a product added to an accumulator that holds kMagicB + s + 65792 r (s = true partial
+    //    sum, r = coefficient sum of the products still to come, BEFORE this one is added:
+    //    r_before = r_after + c for fma.rm, r_after - c ... handled below) gives
+    //    kMagicB + (s + floor(v c / 128)) + 65792 r_after exactly, at the extremes the host-side
+    //    condition biased_order_ok() allows (|r_after| <= kBiasedMaxSuffix, |s| <= 4 * 2^15).
+    for (int c = -128; c <= 127; ++c) {
+        const float kc = (float)c / 128.0f, nkc = -(float)c / 128.0f;
+        for (int v = -32768; v <= 32767; ++v) {
+            const int f = floordiv128(v * c);
+            const float u = biased_from_int(v);
+            if (u != (float)v + kBias16) ++bad;
+            for (int r_after : {-kBiasedMaxSuffix, 0, kBiasedMaxSuffix}) {
+                for (int s4 : {-4 * 32768, 0, 4 * 32768}) {
+                    // '+' product (B taps): the accumulator before it carries -65792 c on top of r_after
+                    const double before_p = (double)kMagicB + s4 - 65792.0 * r_after - 65792.0 * c;
+                    const float got_p = __fmaf_rd(u, kc, (float)before_p);
+                    const double want_p = (double)kMagicB + s4 + f - 65792.0 * r_after;
+                    // '-' product (A taps): carries +65792 c
+                    const double before_m = (double)kMagicB + s4 - 65792.0 * r_after + 65792.0 * c;
+                    const float got_m = __fmaf_ru(u, nkc, (float)before_m);
+                    const double want_m = (double)kMagicB + s4 - f - 65792.0 * r_after;
+                    if ((double)(float)before_p != before_p || (double)(float)before_m != before_m) ++bad;   // start values are exact
+                    if ((double)got_p != want_p || (double)got_m != want_m) {
+                        if (bad < 25) std::printf("biased-step mismatch c=%d v=%d r=%d s=%d\n", c, v, r_after, s4);
+                        ++bad;
+                    }
+                }
+            }
+        }
+    }
+    //    ... and the fixed bank of the reference passes the condition, extreme sets do not
+    if (!biased_order_ok(-14, 0, 14, 107, 21) || !biased_order_ok(-15, 0, 15, 107, -21)) ++bad;
+    if (biased_order_ok(-128, 127, -128, -128, 127) || biased_order_ok(0, 0, 0, 0, 61)) ++bad;
+    // 8. window_biased == window_int + bias for every int16 sample and every ROM value but -32768
+    for (int c = -32767; c <= 32767; ++c)
+        for (int x = -32768; x <= 32767; ++x)
+            if (window_biased(x, 2 * c, 0x4B000000u) != biased_from_int(window_int(x, c))) {
+                if (bad < 30) std::printf("window_biased mismatch x=%d c=%d\n", x, c);
+                ++bad;
+            }
     std::printf("bad=%ld\n", bad);
     return bad ? 1 : 0;
 }

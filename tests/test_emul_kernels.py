@@ -23,6 +23,36 @@ def adversarial(rng, c, n):
     return x
 
 
+def biased_edge_sections(rng):
+    """Six sections on the edge of biased_order_ok() (fra_common.cuh): the coefficient sums of the
+    product-order suffixes (y[n-2] | x[n-2], x[n-1], x[n], y[n-1]) reach +-60, the first product's
+    coefficient (A0) is anything, including -128 / 127."""
+    sec = np.zeros((6, 6), dtype=np.int8)
+    pats = [(60, 0, -60, -128, -60),      # B0, B1, B2, A0, A1: suffixes -A1=60 | B2-A1=0 | B1+..=0 | B0+..=60
+            (-60, 60, -60, 127, 0),       # suffixes 0 | -60 | 0 | -60
+            (0, -120, 120, -1, 60),       # -60 | 60 | -60 | -60
+            (-14, 0, 14, 107, 21),        # the reference's fixed bank
+            (-15, 0, 15, 107, -21),
+            (127, -127, 60, 64, 0)]       # 0 | 60 | -67?  replaced below if not eligible
+    def ok(b0, b1, b2, a0, a1):
+        t = [-a0, b0, b1, b2, -a1]
+        s = 0
+        for k in range(4, 0, -1):
+            s += t[k]
+            if abs(s) > 60:
+                return False
+        return True
+    for i, p in enumerate(pats):
+        if not ok(*p):
+            while True:
+                p = tuple(int(v) for v in rng.integers(-128, 128, 5))
+                if ok(*p):
+                    break
+        sec[i, :5] = p
+    assert all(ok(*[int(v) for v in sec[i, :5]]) for i in range(6))
+    return sec
+
+
 @pytest.mark.parametrize("flags,name", [(_abi.FRA_K1_FORCE_LANE, "lane"), (_abi.FRA_K1_FORCE_SPLIT, "split"),
                                         (_abi.FRA_K1_FORCE_STAGE, "stage"), (_abi.FRA_K1_FORCE_DUO, "duo")])
 @pytest.mark.parametrize("channels", [1, 6, 37])
@@ -319,3 +349,33 @@ def test_stream_exact_and_chunked_modes(rom):
         assert np.array_equal(y, g.window(x[None], rom)[0]) and stats["n_mismatch"] == 0
     finally:
         f.close()
+
+
+@pytest.mark.parametrize("flags", [_abi.FRA_K1_FORCE_LANE, _abi.FRA_K1_FORCE_DUO])
+def test_all_biased_step_at_the_edge_of_its_condition(flags, rom):
+    """biquad_step_biased (every operand carries the PRMT bias, no FADD): coefficient sets on the
+    edge of the eligibility condition, random history, full-range input; and the same through
+    the general step (FRA_K1_NO_BIASED) for the same bits."""
+    rng = np.random.default_rng(77)
+    c, n = 7, 1024
+    for trial in range(3):
+        sec = biased_edge_sections(rng)
+        if trial == 2:
+            sec[:, 1] = 0
+            sec[:, 2] = np.clip(sec[:, 2], -60, 60)
+            sec[:, 4] = np.clip(sec[:, 4], -30, 30)
+            sec[:, 0] = -sec[:, 2]
+        st0 = rng.integers(-32768, 32768, (c, 6, 4)).astype(np.int16)
+        x = adversarial(rng, c, n)
+        y, st = cg.window_iir_sections(x, rom, sec, st0)
+        for fl in (flags, flags | _abi.FRA_K1_NO_BIASED):
+            f = EmulFra(c, n, fl)
+            try:
+                f.load_sections(sec)
+                f.command(bytes([0xA1]))
+                f.set_state(st0)
+                out = f.process(x, continuous=True, want=("filtered",))
+                assert np.array_equal(out["filtered"], y), (trial, fl)
+                assert np.array_equal(f.get_state(), st)
+            finally:
+                f.close()

@@ -499,3 +499,33 @@ def test_magnitude_averaging_in_the_pack_stage(fra, rom):
             assert np.allclose(out["mag"].cpu().numpy(), avg, rtol=1e-6, atol=1e-4)
         with pytest.raises(fra.FraError):
             ctx.set_mag_average(0.0)
+
+
+@pytest.mark.parametrize("variant", ["lane", "duo", "auto"])
+def test_all_biased_step_at_the_edge_of_its_condition(fra, rom, variant):
+    """biquad_step_biased (five FFMAs + one PRMT per stage, every operand carrying the PRMT bias):
+    coefficient sets on the edge of its eligibility condition, random history, full-range input,
+    16K frames over two continuous calls; the general step (FRA_K1_NO_BIASED) gives the same bits."""
+    from tests.test_emul_kernels import biased_edge_sections
+    flags = {"lane": fra._abi.FRA_K1_FORCE_LANE, "duo": fra._abi.FRA_K1_FORCE_DUO, "auto": 0}[variant]
+    rng = np.random.default_rng(78)
+    c, n = 70, 16384
+    for trial in range(3):
+        sec = biased_edge_sections(rng)
+        if trial == 2:
+            sec[:, 1] = 0
+            sec[:, 2] = np.clip(sec[:, 2], -60, 60)
+            sec[:, 4] = np.clip(sec[:, 4], -30, 30)
+            sec[:, 0] = -sec[:, 2]
+        st0 = rng.integers(-32768, 32768, (c, 6, 4)).astype(np.int16)
+        xa, xb = adversarial(rng, c, n), adversarial(rng, c, n)
+        ya, st = cg.window_iir_sections(xa, rom, sec, st0)
+        yb, st = cg.window_iir_sections(xb, rom, sec, st)
+        for fl in (flags, flags | fra._abi.FRA_K1_NO_BIASED):
+            with fra.FraContext(c, n, flags=fl) as ctx:
+                ctx.load_sections(sec)
+                ctx.set_mode(0xA1)
+                ctx.set_state(dev(st0))
+                assert np.array_equal(ctx.process(dev(xa), continuous=True, want=("filtered",))["filtered"].cpu().numpy(), ya)
+                assert np.array_equal(ctx.process(dev(xb), continuous=True, want=("filtered",))["filtered"].cpu().numpy(), yb)
+                assert np.array_equal(ctx.get_state().cpu().numpy(), st)

@@ -18,12 +18,14 @@ ap.add_argument("--mode", default="0x00")
 ap.add_argument("--k1", default="auto")
 ap.add_argument("--time", action="store_true")
 ap.add_argument("--pipeline", action="store_true", help="FRA_PIPELINE context; reports whole-loop throughput")
+ap.add_argument("--flags", type=lambda v: int(v, 0), default=0, help="extra fra_create flags (e.g. 0x80 = FRA_K1_NO_BIASED)")
 ap.add_argument("--hiccup", type=float, default=0.0, help="host sleep (s) every 40 steps inside the timed loop")
 a = ap.parse_args()
 flags = {"auto": 0, "lane": _abi.FRA_K1_FORCE_LANE, "split": _abi.FRA_K1_FORCE_SPLIT,
          "spec": _abi.FRA_K1_SPECULATE | _abi.FRA_K1_FORCE_SPLIT, "stage": _abi.FRA_K1_FORCE_STAGE, "duo": _abi.FRA_K1_FORCE_DUO}[a.k1]
 if a.pipeline:
     flags |= _abi.FRA_PIPELINE
+flags |= a.flags
 ctx = FraContext(a.channels, a.n, flags=flags)
 ctx.command(int(a.mode, 16))
 xs = [synth.tone_noise(a.channels, a.n, "cuda", frame=i) for i in range(2)]
