@@ -27,15 +27,18 @@ def stale():
     return any(os.path.getmtime(f) > t for f in files)
 
 
-def build(force=False, verbose=False):
-    if not force and not stale():
+def build(force=False, verbose=False, out=None, defines=()):
+    """out / defines: experiment builds (tools/build_variants.py) beside the product library."""
+    if out is None and not force and not stale():
         return OUT
+    out = out or OUT
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-           "-DFRA_USE_F32X2", "-shared", "-Xcompiler", "-fPIC", "--cudart", "static", "-o", OUT, SRC]
+           "-DFRA_USE_F32X2", *[f"-D{d}" for d in defines], "-shared", "-Xcompiler", "-fPIC", "--cudart", "static",
+           "-o", out, SRC]
     if verbose:
         cmd[1:1] = ["-Xptxas", "-v"]
     subprocess.check_call(cmd)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

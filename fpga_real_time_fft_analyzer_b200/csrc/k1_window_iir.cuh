@@ -172,20 +172,71 @@ FRA_DEV bool rom_quirk_range(int w0, int len)
     return (w0 < 15) || (w0 + len > 8178 && w0 < 8206) || (w0 + len > 16369);
 }
 
+// One iteration of the skewed cascade: stage s works on sample i - s, so the six stage steps of an
+// iteration are independent of each other (each consumes what its predecessor produced in the
+// PREVIOUS iteration) and a single in-order warp has six dependency chains to interleave instead of
+// one chain through all six stages (75 cycles per sample measured for the sample-major order; the
+// critical path here is one stage step).  Stages are visited last to first so that pipe[s - 1]
+// still holds the previous iteration's value.  Returns the last stage's accumulator (sample i - 5).
+template <bool B1Z>
+FRA_DEV float lane_skewed_iteration(float ux, const CascadeCoef &coef, StageStateB (&st)[kStages], float (&pipe)[kStages])
+{
+    float acc = 0.0f;
+#pragma unroll
+    for (int s = kStages - 1; s >= 0; --s) {
+        const float in = (s == 0) ? ux : pipe[s - 1];
+        const float r = biquad_step_biased<B1Z>(in, coef.set[s], st[s], &pipe[s]);
+        if (s == kStages - 1) acc = r;
+    }
+    return acc;
+}
+
+constexpr int kLaneLag = kStages - 1;      // the last stage emits sample i - 5 at iteration i
+
+// One trip of 16 iterations i0 .. i0 + 15.  FIRST (i0 = 0): stage s sees its first real sample at
+// iteration s; what it computed before that is junk, so its history is (re)loaded right there - no
+// guard anywhere.  The accumulators of samples i0 - 5 .. i0 + 10 come out; with the three carried
+// from the trip before (i0 - 8 .. i0 - 6) they complete the 16-byte groups [i0 - 8, i0) and
+// [i0, i0 + 8); the last three are carried on.
+template <bool B1Z, bool FIRST>
+FRA_DEV void lane_trip16(const K1Args &a, size_t c, const float (&u)[16], StageStateB (&st)[kStages], float (&pipe)[kStages],
+                         float (&carry)[3], uint4 &ga, uint4 &gb)
+{
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        if (FIRST && j < kStages) st[j] = load_state_biased(a.state, c, j, a.continuous != 0);
+        acc[j] = lane_skewed_iteration<B1Z>(u[j], a.coef, st, pipe);
+    }
+    ga.x = pack16_acc(carry[0], carry[1]);
+    ga.y = pack16_acc(carry[2], acc[0]);
+    ga.z = pack16_acc(acc[1], acc[2]);
+    ga.w = pack16_acc(acc[3], acc[4]);
+    gb.x = pack16_acc(acc[5], acc[6]);
+    gb.y = pack16_acc(acc[7], acc[8]);
+    gb.z = pack16_acc(acc[9], acc[10]);
+    gb.w = pack16_acc(acc[11], acc[12]);
+    carry[0] = acc[13]; carry[1] = acc[14]; carry[2] = acc[15];
+}
+
 template <bool B1Z>
 __global__ void __launch_bounds__(kLaneBlock) k1_lane_biased(K1Args a)
 {
     const int c_raw = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = c_raw < a.channels;
-    const int c = live ? c_raw : a.channels - 1;     // inactive lanes shadow the last channel (no stores)
+    const size_t c = (size_t)(live ? c_raw : a.channels - 1);     // inactive lanes shadow the last channel (no stores)
     const unsigned exp23 = a.coef.set[0].exp23;
 
     StageStateB st[kStages];
+    float pipe[kStages], carry[3] = {0.0f, 0.0f, 0.0f};
 #pragma unroll
-    for (int s = 0; s < kStages; ++s) st[s] = load_state_biased(a.state, (size_t)c, s, a.continuous != 0);
+    for (int s = 0; s < kStages; ++s) {
+        st[s].x1 = st[s].x2 = st[s].y1 = st[s].y2 = kBias16;      // junk phase of the first trip: any finite value
+        pipe[s] = kBias16;
+    }
 
-    const int16_t *src = a.in + (size_t)c * a.n;
-    int16_t *dst = a.out + (size_t)c * a.n;
+    const int16_t *src = a.in + c * a.n;
+    int16_t *dst = a.out + c * a.n;
 
     __shared__ uint4 stage_x[2][2][kLaneBlock];      // [buffer][half][lane]: 16 samples per lane
     __shared__ int4 stage_rom[2][4];                 // [buffer][4 x 4 doubled ROM entries]
@@ -196,48 +247,61 @@ __global__ void __launch_bounds__(kLaneBlock) k1_lane_biased(K1Args a)
         if (lane < 4) cp_async16(&stage_rom[b][lane], a.rom2x + ((n0 + 4 * lane) & (kWindowLen - 1)));
         cp_async_commit();
     };
-    request(0, 0);
-    for (int n0 = 0, it = 0; n0 < a.n; n0 += 16, ++it) {
-        const int b = it & 1;
+    // samples [n0, n0 + 16) of this lane's channel -> window -> biased floats
+    auto fetch = [&](int n0, int b, float (&u)[16]) {
         if (n0 + 16 < a.n) request(n0 + 16, b ^ 1);
         else cp_async_commit();
         cp_async_wait<1>();
         __syncwarp();                                 // the ROM words were copied by lanes 0..3
         const uint4 xa = stage_x[b][0][lane], xb = stage_x[b][1][lane];
         const int4 r0 = stage_rom[b][0], r1 = stage_rom[b][1], r2 = stage_rom[b][2], r3 = stage_rom[b][3];
-        float u[16];
-        {
-            float ua[8], ub[8];
-            if (rom_quirk_range(n0 & (kWindowLen - 1), 16)) {      // warp-uniform
-                window8_biased<true>(xa, r0, r1, exp23, ua);
-                window8_biased<true>(xb, r2, r3, exp23, ub);
-            } else {
-                window8_biased<false>(xa, r0, r1, exp23, ua);
-                window8_biased<false>(xb, r2, r3, exp23, ub);
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { u[j] = ua[j]; u[8 + j] = ub[j]; }
+        float ua[8], ub[8];
+        if (rom_quirk_range(n0 & (kWindowLen - 1), 16)) {      // warp-uniform
+            window8_biased<true>(xa, r0, r1, exp23, ua);
+            window8_biased<true>(xb, r2, r3, exp23, ub);
+        } else {
+            window8_biased<false>(xa, r0, r1, exp23, ua);
+            window8_biased<false>(xb, r2, r3, exp23, ub);
         }
-        unsigned ow[8];
 #pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-            float v0 = u[j], v1 = u[j + 1], acc0 = 0.0f, acc1 = 0.0f;
-#pragma unroll
-            for (int s = 0; s < kStages; ++s) acc0 = biquad_step_biased<B1Z>(v0, a.coef.set[s], st[s], &v0);
-#pragma unroll
-            for (int s = 0; s < kStages; ++s) acc1 = biquad_step_biased<B1Z>(v1, a.coef.set[s], st[s], &v1);
-            ow[j >> 1] = pack16_acc(acc0, acc1);
-        }
-        if (live) {
-            stg128(dst + n0, make_uint4(ow[0], ow[1], ow[2], ow[3]));
-            stg128(dst + n0 + 8, make_uint4(ow[4], ow[5], ow[6], ow[7]));
-        }
+        for (int j = 0; j < 8; ++j) { u[j] = ua[j]; u[8 + j] = ub[j]; }
         __syncwarp();                                 // everyone has read buffer b before it is refilled
-    }
+    };
 
-    if (live) {
+    request(0, 0);
+    uint4 ga, gb;
+    {
+        float u[16];
+        fetch(0, 0, u);
+        lane_trip16<B1Z, true>(a, c, u, st, pipe, carry, ga, gb);
+        if (live) stg128(dst, gb);                     // samples 0..7; the group before them does not exist
+    }
+#pragma unroll 1
+    for (int n0 = 16, it = 1; n0 < a.n; n0 += 16, ++it) {
+        float u[16];
+        fetch(n0, it & 1, u);
+        lane_trip16<B1Z, false>(a, c, u, st, pipe, carry, ga, gb);
+        if (live) {
+            stg128(dst + n0 - 8, ga);
+            stg128(dst + n0, gb);
+        }
+    }
+    // drain: iterations n .. n + 4 push samples n - 5 .. n - 1 through the remaining stages.  Stage s saw
+    // its last real sample at iteration n - 1 + s: its history is final (and stored) right after that;
+    // what it computes later is junk and goes nowhere.
+    if (live) store_state_biased(a.state, c, 0, st[0]);
+    float tail[kLaneLag];
 #pragma unroll
-        for (int s = 0; s < kStages; ++s) store_state_biased(a.state, (size_t)c, s, st[s]);
+    for (int j = 0; j < kLaneLag; ++j) {
+        tail[j] = lane_skewed_iteration<B1Z>(kBias16, a.coef, st, pipe);
+        if (live) store_state_biased(a.state, c, j + 1, st[j + 1]);
+    }
+    if (live) {
+        ga.x = pack16_acc(carry[0], carry[1]);
+        ga.y = pack16_acc(carry[2], tail[0]);
+        ga.z = pack16_acc(tail[1], tail[2]);
+        ga.w = pack16_acc(tail[3], tail[4]);
+        stg128(dst + a.n - 8, ga);
     }
 }
 

@@ -22,6 +22,15 @@
 
 namespace fra {
 
+// pass 0 of the 16K kernel: one 64-bit load per row for the thread's two butterflies (1) or two 32-bit loads (0)
+#ifndef FRA_K2_PAIRED
+#define FRA_K2_PAIRED 1
+#endif
+// resident CTAs per SM the FFT kernel is compiled for (register cap 65536 / (256 * this))
+#ifndef FRA_K2_MINBLOCKS
+#define FRA_K2_MINBLOCKS 3
+#endif
+
 struct K2Args {
     const uint32_t *in;     // [B][N/2] words = int16 pairs
     const int *rom32;       // window ROM (WIN only)
@@ -57,13 +66,13 @@ struct FftPlan {
     static constexpr int SLOTS = FPC * (L / 2);                 // last-pass work items per CTA
 };
 
-// two packed int16 -> two exact floats with no conversion instruction: flip the sign
-// bits (offset-binary), splice each half under the exponent of 2^23, subtract 2^23 + 2^15
+// two packed int16 -> two floats: one I2F.S16 each, reading the register's low / high half
+// directly (conversion unit; two issue slots per pair instead of the five of an ALU/FMA-pipe
+// unpack - XOR, two PRMT, two FADD - and the FFT kernels are issue-bound)
 FRA_DEV float2 int16_pair_to_float2(unsigned w, unsigned exp23)
 {
-    const unsigned u = w ^ 0x80008000u;
-    return make_float2(__uint_as_float(__byte_perm(u, exp23, 0x7610)) - kBias16,
-                       __uint_as_float(__byte_perm(u, exp23, 0x7632)) - kBias16);
+    (void)exp23;
+    return make_float2((float)(short)(w & 0xFFFFu), (float)(short)(w >> 16));
 }
 
 // complex add / subtract as ONE packed fp32x2 instruction (Blackwell FADD2): same FP32 pipe
@@ -224,10 +233,104 @@ FRA_DEV float2 w16(int q)
     }
 }
 
+// One radix-16 Stockham pass of the whole CTA (two butterflies per thread), PASS a compile-time
+// constant.  Pass 0 reads the int16 frame from global memory, the others read shared memory; the
+// last pass of each size writes back to the positions it read, only the middle pass of L = 4096
+// scatters into other threads' read positions and needs a barrier between read and write.
+template <int LOG2N, bool WIN, int PASS>
+FRA_DEV void fft_pass(const K2Args &a, float2 *buf, int tid, int frame0)
+{
+    using P = FftPlan<LOG2N>;
+    constexpr int IPT = P::ITEMS / P::THREADS;          // butterflies per thread per pass (2)
+    // N = 16384: THREADS = NB and F = 2, so a thread's two butterflies are column j = tid of the
+    // sub-sequences f = 0 and f = 1, whose input words are adjacent: one 64-bit load for both
+    constexpr bool PAIRED = FRA_K2_PAIRED && (PASS == 0) && (P::F == 2) && (P::THREADS == P::NB) && (IPT == 2) && (P::FPC == 1);
+    float2 o[IPT][16];
+    int wbase[IPT];                                    // swizzled base of this butterfly's outputs
+    int jlow[IPT];
+    uint2 pre[PAIRED ? 16 : 1];
+    if constexpr (PAIRED) {
+        const bool live = frame0 < a.batch;
+        const uint2 *src = reinterpret_cast<const uint2 *>(a.in + (size_t)frame0 * P::M) + tid;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) pre[r] = live ? __ldg(src + P::NB * r) : make_uint2(0u, 0u);   // z[2 (j + NB r) + {0, 1}]
+    }
+#pragma unroll
+    for (int q = 0; q < IPT; ++q) {
+        const int it = tid + P::THREADS * q;
+        const int j = it % P::NB;
+        const int f = (it / P::NB) % P::F;
+        const int fr = it / (P::NB * P::F);
+        const int base = fr * P::M + f * P::L;
+        float2 v[16];
+        if (PASS == 0) {
+            const int frame = frame0 + fr;
+            const bool live = frame < a.batch;
+            const uint32_t *src = a.in + (size_t)frame * P::M + (P::F * j + f);
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                unsigned w;
+                if constexpr (PAIRED) w = (q == 0) ? pre[r].x : pre[r].y;
+                else w = live ? __ldg(src + P::F * P::NB * r) : 0u;      // z[F (j + NB r) + f]
+                if (WIN) {
+                    const int e = P::F * (j + P::NB * r) + f;
+                    const int2 c = __ldg(reinterpret_cast<const int2 *>(a.rom32 + ((2 * e) & (kWindowLen - 1))));
+                    v[r] = make_float2(small_int_to_float(window_int(lo16(w), c.x)),
+                                       small_int_to_float(window_int(hi16(w), c.y)));
+                } else {
+                    v[r] = int16_pair_to_float2(w, a.exp23);
+                }
+            }
+            wbase[q] = base + 16 * j;                  // out[16 j + r]
+            jlow[q] = j & 7;
+        } else {
+            constexpr int ns = (PASS == 1) ? 16 : 256;
+            const int k = j % ns;
+            const float2 *tw = (PASS == 1) ? (a.tw1 + k) : (a.tw2 + k);
+            float2 t[16];
+#pragma unroll
+            for (int r = 1; r < 16; ++r) t[r] = __ldg(tw + r * ns);
+            // in[j + NB r].  NB = 256: 256 r is a whole number of 8-row groups, one swizzled base.
+            // NB = 16 (L = 256): j < 16 is the column, row r: chunk XOR is r & 7.
+            const float2 *p = buf + swz(base + j);
+            const float2 *prow = buf + base;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                const float2 x = (P::NB == 256) ? p[256 * r] : prow[16 * r + (j ^ ((r & 7) << 1))];
+                v[r] = (r > 0) ? cmul(x, t[r]) : x;
+            }
+            wbase[q] = base + (j / ns) * ns * 16 + k;  // out[.. + r ns]
+            jlow[q] = k;
+        }
+        dft16(v, o[q]);
+    }
+    if (PASS == 1 && P::PASSES == 3) __syncthreads();
+#pragma unroll
+    for (int q = 0; q < IPT; ++q) {
+        if (PASS == 0) {
+            // 16 consecutive elements = one 128-byte row: eight 16-byte stores, chunk c -> c ^ (row & 7)
+            float4 *row = reinterpret_cast<float4 *>(buf + wbase[q]);
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                row[c ^ jlow[q]] = make_float4(o[q][2 * c].x, o[q][2 * c].y, o[q][2 * c + 1].x, o[q][2 * c + 1].y);
+        } else if (PASS == 1) {
+            // out[w + 16 r], w = (8-row-aligned) + k with k < 16: row advances by r, chunk XOR is r & 7
+            float2 *prow = buf + (wbase[q] - jlow[q]);
+#pragma unroll
+            for (int r = 0; r < 16; ++r) prow[16 * r + (jlow[q] ^ ((r & 7) << 1))] = o[q][r];
+        } else {
+            float2 *p = buf + swz(wbase[q]);           // out[j + 256 r]: same positions as read
+#pragma unroll
+            for (int r = 0; r < 16; ++r) p[256 * r] = o[q][r];
+        }
+    }
+    __syncthreads();
+}
+
 // OUT = 0: int16 frames only (the hot configuration); OUT = 1: any combination of
 // outputs, selected at run time by the null pointers in K2Args.
 template <int LOG2N, bool WIN, int QMODE, int OUT>
-__global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS, (LOG2N == 15) ? 1 : 3) k2_fft(K2Args a)
+__global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS, (LOG2N == 15) ? 1 : FRA_K2_MINBLOCKS) k2_fft(K2Args a)
 {
     using P = FftPlan<LOG2N>;
     constexpr int IPT = P::ITEMS / P::THREADS;          // butterflies per thread per pass (2)
@@ -240,84 +343,11 @@ __global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS, (LOG2N == 15) ? 1 : 3
 #endif
 
     // ---------------------------------------------- radix-16 Stockham passes
-#pragma unroll 1
-    for (int pass = 0; pass < P::PASSES; ++pass) {
-        float2 o[IPT][16];
-        int wbase[IPT];                                    // swizzled base of this butterfly's outputs
-        int jlow[IPT];
-#pragma unroll
-        for (int q = 0; q < IPT; ++q) {
-            const int it = tid + P::THREADS * q;
-            const int j = it % P::NB;
-            const int f = (it / P::NB) % P::F;
-            const int fr = it / (P::NB * P::F);
-            const int base = fr * P::M + f * P::L;
-            float2 v[16];
-            if (pass == 0) {
-                const int frame = frame0 + fr;
-                const bool live = frame < a.batch;
-                const uint32_t *src = a.in + (size_t)frame * P::M + (P::F * j + f);
-#pragma unroll
-                for (int r = 0; r < 16; ++r) {
-                    const unsigned w = live ? __ldg(src + P::F * P::NB * r) : 0u;   // z[F (j + NB r) + f]
-                    if (WIN) {
-                        const int e = P::F * (j + P::NB * r) + f;
-                        const int2 c = __ldg(reinterpret_cast<const int2 *>(a.rom32 + ((2 * e) & (kWindowLen - 1))));
-                        v[r] = make_float2(small_int_to_float(window_int(lo16(w), c.x)),
-                                           small_int_to_float(window_int(hi16(w), c.y)));
-                    } else {
-                        v[r] = int16_pair_to_float2(w, a.exp23);
-                    }
-                }
-                wbase[q] = base + 16 * j;                  // out[16 j + r]
-                jlow[q] = j & 7;
-            } else {
-                const int ns = (pass == 1) ? 16 : 256;
-                const int k = j % ns;
-                const float2 *tw = (pass == 1) ? (a.tw1 + k) : (a.tw2 + k);
-                const int tws = (pass == 1) ? 16 : 256;
-                float2 t[16];
-#pragma unroll
-                for (int r = 1; r < 16; ++r) t[r] = __ldg(tw + r * tws);
-                // in[j + NB r].  NB = 256: 256 r is a whole number of 8-row groups, one swizzled base.
-                // NB = 16 (L = 256): j < 16 is the column, row r: chunk XOR is r & 7.
-                const float2 *p = buf + swz(base + j);
-                const float2 *prow = buf + base;
-#pragma unroll
-                for (int r = 0; r < 16; ++r) {
-                    const float2 x = (P::NB == 256) ? p[256 * r] : prow[16 * r + (j ^ ((r & 7) << 1))];
-                    v[r] = (r > 0) ? cmul(x, t[r]) : x;
-                }
-                wbase[q] = base + (j / ns) * ns * 16 + k;  // out[.. + r ns]
-                jlow[q] = k;
-            }
-            dft16(v, o[q]);
-        }
-        // pass 0 reads global memory only; the last pass of each size writes back
-        // to the positions it read.  Only the middle pass of L = 4096 scatters into
-        // other threads' read positions and needs the barrier between read and write.
-        if (pass == 1 && P::PASSES == 3) __syncthreads();
-#pragma unroll
-        for (int q = 0; q < IPT; ++q) {
-            if (pass == 0) {
-                // 16 consecutive elements = one 128-byte row: eight 16-byte stores, chunk c -> c ^ (row & 7)
-                float4 *row = reinterpret_cast<float4 *>(buf + wbase[q]);
-#pragma unroll
-                for (int c = 0; c < 8; ++c)
-                    row[c ^ jlow[q]] = make_float4(o[q][2 * c].x, o[q][2 * c].y, o[q][2 * c + 1].x, o[q][2 * c + 1].y);
-            } else if (pass == 1) {
-                // out[w + 16 r], w = (8-row-aligned) + k with k < 16: row advances by r, chunk XOR is r & 7
-                float2 *prow = buf + (wbase[q] - jlow[q]);
-#pragma unroll
-                for (int r = 0; r < 16; ++r) prow[16 * r + (jlow[q] ^ ((r & 7) << 1))] = o[q][r];
-            } else {
-                float2 *p = buf + swz(wbase[q]);           // out[j + 256 r]: same positions as read
-#pragma unroll
-                for (int r = 0; r < 16; ++r) p[256 * r] = o[q][r];
-            }
-        }
-        __syncthreads();
-    }
+    // (compile-time pass index: twiddle strides, swizzled offsets and the pass-specific store
+    // pattern are all immediates; a run-time pass loop cost ~4 issue slots per sample)
+    fft_pass<LOG2N, WIN, 0>(a, buf, tid, frame0);
+    fft_pass<LOG2N, WIN, 1>(a, buf, tid, frame0);
+    if (P::PASSES == 3) fft_pass<LOG2N, WIN, 2>(a, buf, tid, frame0);
 
     // ---------------- last pass: radix-F combine + untangle + mirror + pack
     BinOut out;
