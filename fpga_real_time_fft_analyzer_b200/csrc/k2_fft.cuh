@@ -26,9 +26,11 @@ namespace fra {
 #ifndef FRA_K2_PAIRED
 #define FRA_K2_PAIRED 1
 #endif
-// resident CTAs per SM the FFT kernel is compiled for (register cap 65536 / (256 * this))
+// resident CTAs per SM the FFT kernel is compiled for (register cap 65536 / (256 * this)).  With the
+// passes unrolled and both butterflies' input words in flight the kernel wants ~100 registers: at 3 CTAs
+// per SM (80 registers) it spills 250 bytes and runs 2.00 ms per 65536 frames, at 2 (no spills) 1.62 ms.
 #ifndef FRA_K2_MINBLOCKS
-#define FRA_K2_MINBLOCKS 3
+#define FRA_K2_MINBLOCKS 2
 #endif
 
 struct K2Args {
