@@ -35,6 +35,7 @@ FRA_K1_FORCE_STAGE = 0x10
 FRA_K1_FORCE_DUO = 0x20
 FRA_PIPELINE = 0x40
 FRA_K1_NO_BIASED = 0x80
+FRA_K2_NO_STAGED = 0x100
 
 
 class FraOutputs(C.Structure):

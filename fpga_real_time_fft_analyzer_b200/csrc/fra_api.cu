@@ -202,6 +202,21 @@ int launch_k2_inst(fra_ctx *ctx, const K2Args &args, cudaStream_t st)
     using P = FftPlan<LOG2N>;
     // frames-only is the hot configuration and gets its own instantiation
     const bool frames_only = args.frames && !args.iq && !args.mag && !args.phase;
+    if constexpr (LOG2N == kStagedLog2N) {
+        // 16K frames: persistent CTAs, each frame staged by one bulk copy (k2_fft.cuh).  The bulk copy needs a
+        // 16-byte aligned source; a pipelined context keeps the one-frame-per-CTA kernel, whose CTAs come and
+        // go and leave room for the window+IIR kernel's CTAs beside them.
+        const bool staged = !(ctx->flags & (FRA_K2_NO_STAGED | FRA_PIPELINE)) && (reinterpret_cast<uintptr_t>(args.in) % 16) == 0;
+        if (staged && args.batch > 0) {
+            auto sfn = frames_only ? k2_fft_staged<WIN, QMODE, 0> : k2_fft_staged<WIN, QMODE, 1>;
+            FRA_SMEM(ctx, sfn, kStagedSmemBytes);
+            const int grid = std::min(args.batch, FRA_K2_MINBLOCKS * std::max(1, ctx->sm_count));
+            FRA_LAUNCH(sfn, dim3(grid), dim3(P::THREADS), (size_t)kStagedSmemBytes, st, args);
+            FRA_TRY(ctx, cudaGetLastError());
+            ctx->last_kernels++;
+            return FRA_OK;
+        }
+    }
     auto kfn = frames_only ? k2_fft<LOG2N, WIN, QMODE, 0> : k2_fft<LOG2N, WIN, QMODE, 1>;
     FRA_SMEM(ctx, kfn, P::SMEM_BYTES);
     const int grid = (args.batch + P::FPC - 1) / P::FPC;
@@ -392,9 +407,10 @@ int process_range(fra_ctx *ctx, const int16_t *d_in, int c0, int nch, int contin
             FRA_SMEM(ctx, kfn, (int)smem);
             FRA_LAUNCH(kfn, dim3(grid), dim3(kSplitWarps * 32), smem, st, k1);
         } else {
-            const int grid = (nch + kLaneBlock - 1) / kLaneBlock;
+            const int block = biased ? kLaneBiasedBlock : kLaneBlock;
+            const int grid = (nch + block - 1) / block;
             auto kfn = biased ? (b1z ? k1_lane_biased<true> : k1_lane_biased<false>) : (b1z ? k1_lane<true> : k1_lane<false>);
-            FRA_LAUNCH(kfn, dim3(grid), dim3(kLaneBlock), (size_t)0, st, k1);
+            FRA_LAUNCH(kfn, dim3(grid), dim3(block), (size_t)0, st, k1);
         }
         FRA_TRY(ctx, cudaGetLastError());
         if (ctx->profiling) {

@@ -219,8 +219,14 @@ FRA_DEV void lane_trip16(const K1Args &a, size_t c, const float (&u)[16], StageS
     carry[0] = acc[13]; carry[1] = acc[14]; carry[2] = acc[15];
 }
 
+// Four warps per CTA: a CTA's warps go to the four schedulers of its SM one each (warp id mod 4), so
+// the channels spread evenly over the 592 schedulers by construction.  (With one-warp CTAs the SM's
+// instruction rate stopped rising at ~1.9 per cycle however many CTAs were resident - 16384 channels:
+// 1.76, 65536: 1.9, profiles/r02_k1_lane_16384ch.txt.)
+constexpr int kLaneBiasedBlock = 128;
+
 template <bool B1Z>
-__global__ void __launch_bounds__(kLaneBlock) k1_lane_biased(K1Args a)
+__global__ void __launch_bounds__(kLaneBiasedBlock) k1_lane_biased(K1Args a)
 {
     const int c_raw = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = c_raw < a.channels;
@@ -238,13 +244,13 @@ __global__ void __launch_bounds__(kLaneBlock) k1_lane_biased(K1Args a)
     const int16_t *src = a.in + c * a.n;
     int16_t *dst = a.out + c * a.n;
 
-    __shared__ uint4 stage_x[2][2][kLaneBlock];      // [buffer][half][lane]: 16 samples per lane
-    __shared__ int4 stage_rom[2][4];                 // [buffer][4 x 4 doubled ROM entries]
-    const int lane = threadIdx.x;
+    __shared__ uint4 stage_x[2][2][kLaneBiasedBlock];          // [buffer][half][thread]: 16 samples per lane
+    __shared__ int4 stage_rom[kLaneBiasedBlock / 32][2][4];    // [warp][buffer][4 x 4 doubled ROM entries]: the warps of a CTA drift apart
+    const int lane = threadIdx.x & 31, tix = threadIdx.x, wrp = threadIdx.x >> 5;
     auto request = [&](int n0, int b) {
-        cp_async16(&stage_x[b][0][lane], src + n0);
-        cp_async16(&stage_x[b][1][lane], src + n0 + 8);
-        if (lane < 4) cp_async16(&stage_rom[b][lane], a.rom2x + ((n0 + 4 * lane) & (kWindowLen - 1)));
+        cp_async16(&stage_x[b][0][tix], src + n0);
+        cp_async16(&stage_x[b][1][tix], src + n0 + 8);
+        if (lane < 4) cp_async16(&stage_rom[wrp][b][lane], a.rom2x + ((n0 + 4 * lane) & (kWindowLen - 1)));
         cp_async_commit();
     };
     // samples [n0, n0 + 16) of this lane's channel -> window -> biased floats
@@ -253,8 +259,8 @@ __global__ void __launch_bounds__(kLaneBlock) k1_lane_biased(K1Args a)
         else cp_async_commit();
         cp_async_wait<1>();
         __syncwarp();                                 // the ROM words were copied by lanes 0..3
-        const uint4 xa = stage_x[b][0][lane], xb = stage_x[b][1][lane];
-        const int4 r0 = stage_rom[b][0], r1 = stage_rom[b][1], r2 = stage_rom[b][2], r3 = stage_rom[b][3];
+        const uint4 xa = stage_x[b][0][tix], xb = stage_x[b][1][tix];
+        const int4 r0 = stage_rom[wrp][b][0], r1 = stage_rom[wrp][b][1], r2 = stage_rom[wrp][b][2], r3 = stage_rom[wrp][b][3];
         float ua[8], ub[8];
         if (rom_quirk_range(n0 & (kWindowLen - 1), 16)) {      // warp-uniform
             window8_biased<true>(xa, r0, r1, exp23, ua);

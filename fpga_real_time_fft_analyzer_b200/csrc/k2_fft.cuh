@@ -29,6 +29,11 @@ namespace fra {
 // resident CTAs per SM the FFT kernel is compiled for (register cap 65536 / (256 * this)).  With the
 // passes unrolled and both butterflies' input words in flight the kernel wants ~100 registers: at 3 CTAs
 // per SM (80 registers) it spills 250 bytes and runs 2.00 ms per 65536 frames, at 2 (no spills) 1.62 ms.
+// butterfly order in the passes without a read/write hazard: 0 = both butterflies of a thread in flight,
+// 1 = one after the other (unrolled), 2 = one after the other in a rolled loop (fewest registers)
+#ifndef FRA_K2_SEQ
+#define FRA_K2_SEQ 0
+#endif
 #ifndef FRA_K2_MINBLOCKS
 #define FRA_K2_MINBLOCKS 2
 #endif
@@ -240,25 +245,33 @@ FRA_DEV float2 w16(int q)
 // last pass of each size writes back to the positions it read, only the middle pass of L = 4096
 // scatters into other threads' read positions and needs a barrier between read and write.
 template <int LOG2N, bool WIN, int PASS>
-FRA_DEV void fft_pass(const K2Args &a, float2 *buf, int tid, int frame0)
+FRA_DEV void fft_pass(const K2Args &a, float2 *buf, int tid, int frame0, const uint2 *staged = nullptr)
 {
     using P = FftPlan<LOG2N>;
     constexpr int IPT = P::ITEMS / P::THREADS;          // butterflies per thread per pass (2)
     // N = 16384: THREADS = NB and F = 2, so a thread's two butterflies are column j = tid of the
     // sub-sequences f = 0 and f = 1, whose input words are adjacent: one 64-bit load for both
     constexpr bool PAIRED = FRA_K2_PAIRED && (PASS == 0) && (P::F == 2) && (P::THREADS == P::NB) && (IPT == 2) && (P::FPC == 1);
-    float2 o[IPT][16];
-    int wbase[IPT];                                    // swizzled base of this butterfly's outputs
-    int jlow[IPT];
+    // the middle pass of L = 4096 scatters into other threads' read positions: all reads, a barrier, all
+    // writes (both butterflies' outputs live across it).  Every other pass writes where nobody else reads
+    // in that pass (pass 0 reads global memory; the last pass of each size writes back to the positions
+    // it read), so a butterfly can be stored before the next one is loaded.
+    constexpr bool HAZARD = (PASS == 1 && P::PASSES == 3);
     uint2 pre[PAIRED ? 16 : 1];
     if constexpr (PAIRED) {
-        const bool live = frame0 < a.batch;
-        const uint2 *src = reinterpret_cast<const uint2 *>(a.in + (size_t)frame0 * P::M) + tid;
+        if (staged != nullptr) {
+            // the frame was brought into shared memory by a bulk copy (k2_fft_staged): unit-stride 8-byte reads
 #pragma unroll
-        for (int r = 0; r < 16; ++r) pre[r] = live ? __ldg(src + P::NB * r) : make_uint2(0u, 0u);   // z[2 (j + NB r) + {0, 1}]
+            for (int r = 0; r < 16; ++r) pre[r] = staged[tid + P::NB * r];
+        } else {
+            const bool live = frame0 < a.batch;
+            const uint2 *src = reinterpret_cast<const uint2 *>(a.in + (size_t)frame0 * P::M) + tid;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) pre[r] = live ? __ldg(src + P::NB * r) : make_uint2(0u, 0u);   // z[2 (j + NB r) + {0, 1}]
+        }
     }
-#pragma unroll
-    for (int q = 0; q < IPT; ++q) {
+    // butterfly q of this thread: inputs (+ twiddles) -> 16-point DFT in o; wbase / jlow describe where it goes
+    auto compute = [&](int q, float2 (&o)[16], int &wbase, int &jlow) {
         const int it = tid + P::THREADS * q;
         const int j = it % P::NB;
         const int f = (it / P::NB) % P::F;
@@ -283,8 +296,8 @@ FRA_DEV void fft_pass(const K2Args &a, float2 *buf, int tid, int frame0)
                     v[r] = int16_pair_to_float2(w, a.exp23);
                 }
             }
-            wbase[q] = base + 16 * j;                  // out[16 j + r]
-            jlow[q] = j & 7;
+            wbase = base + 16 * j;                     // out[16 j + r]
+            jlow = j & 7;
         } else {
             constexpr int ns = (PASS == 1) ? 16 : 256;
             const int k = j % ns;
@@ -301,29 +314,52 @@ FRA_DEV void fft_pass(const K2Args &a, float2 *buf, int tid, int frame0)
                 const float2 x = (P::NB == 256) ? p[256 * r] : prow[16 * r + (j ^ ((r & 7) << 1))];
                 v[r] = (r > 0) ? cmul(x, t[r]) : x;
             }
-            wbase[q] = base + (j / ns) * ns * 16 + k;  // out[.. + r ns]
-            jlow[q] = k;
+            wbase = base + (j / ns) * ns * 16 + k;     // out[.. + r ns]
+            jlow = k;
         }
-        dft16(v, o[q]);
-    }
-    if (PASS == 1 && P::PASSES == 3) __syncthreads();
-#pragma unroll
-    for (int q = 0; q < IPT; ++q) {
+        dft16(v, o);
+    };
+    auto store = [&](const float2 (&o)[16], int wbase, int jlow) {
         if (PASS == 0) {
             // 16 consecutive elements = one 128-byte row: eight 16-byte stores, chunk c -> c ^ (row & 7)
-            float4 *row = reinterpret_cast<float4 *>(buf + wbase[q]);
+            float4 *row = reinterpret_cast<float4 *>(buf + wbase);
 #pragma unroll
             for (int c = 0; c < 8; ++c)
-                row[c ^ jlow[q]] = make_float4(o[q][2 * c].x, o[q][2 * c].y, o[q][2 * c + 1].x, o[q][2 * c + 1].y);
+                row[c ^ jlow] = make_float4(o[2 * c].x, o[2 * c].y, o[2 * c + 1].x, o[2 * c + 1].y);
         } else if (PASS == 1) {
             // out[w + 16 r], w = (8-row-aligned) + k with k < 16: row advances by r, chunk XOR is r & 7
-            float2 *prow = buf + (wbase[q] - jlow[q]);
+            float2 *prow = buf + (wbase - jlow);
 #pragma unroll
-            for (int r = 0; r < 16; ++r) prow[16 * r + (jlow[q] ^ ((r & 7) << 1))] = o[q][r];
+            for (int r = 0; r < 16; ++r) prow[16 * r + (jlow ^ ((r & 7) << 1))] = o[r];
         } else {
-            float2 *p = buf + swz(wbase[q]);           // out[j + 256 r]: same positions as read
+            float2 *p = buf + swz(wbase);              // out[j + 256 r]: same positions as read
 #pragma unroll
-            for (int r = 0; r < 16; ++r) p[256 * r] = o[q][r];
+            for (int r = 0; r < 16; ++r) p[256 * r] = o[r];
+        }
+    };
+    if (HAZARD || FRA_K2_SEQ == 0) {
+        float2 o[IPT][16];
+        int wbase[IPT], jlow[IPT];
+#pragma unroll
+        for (int q = 0; q < IPT; ++q) compute(q, o[q], wbase[q], jlow[q]);
+        if (HAZARD) __syncthreads();
+#pragma unroll
+        for (int q = 0; q < IPT; ++q) store(o[q], wbase[q], jlow[q]);
+    } else if (FRA_K2_SEQ == 2 && !PAIRED) {
+#pragma unroll 1
+        for (int q = 0; q < IPT; ++q) {
+            float2 o[16];
+            int wbase, jlow;
+            compute(q, o, wbase, jlow);
+            store(o, wbase, jlow);
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < IPT; ++q) {
+            float2 o[16];
+            int wbase, jlow;
+            compute(q, o, wbase, jlow);
+            store(o, wbase, jlow);
         }
     }
     __syncthreads();
@@ -331,25 +367,11 @@ FRA_DEV void fft_pass(const K2Args &a, float2 *buf, int tid, int frame0)
 
 // OUT = 0: int16 frames only (the hot configuration); OUT = 1: any combination of
 // outputs, selected at run time by the null pointers in K2Args.
-template <int LOG2N, bool WIN, int QMODE, int OUT>
-__global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS, (LOG2N == 15) ? 1 : FRA_K2_MINBLOCKS) k2_fft(K2Args a)
+// the last pass of the CTA's frames [frame0, frame0 + FPC): radix-F combine, untangle, mirror, pack
+template <int LOG2N, int QMODE, int OUT>
+FRA_DEV void fft_last_pass(const K2Args &a, const float2 *buf, int tid, int frame0)
 {
     using P = FftPlan<LOG2N>;
-    constexpr int IPT = P::ITEMS / P::THREADS;          // butterflies per thread per pass (2)
-    FRA_DYN_SMEM(smem_raw);
-    float2 *buf = reinterpret_cast<float2 *>(smem_raw);
-    const int tid = threadIdx.x;
-    const int frame0 = blockIdx.x * P::FPC;
-#ifdef FRA_TIMELINE
-    timeline_mark(2, a.tl_step);
-#endif
-
-    // ---------------------------------------------- radix-16 Stockham passes
-    // (compile-time pass index: twiddle strides, swizzled offsets and the pass-specific store
-    // pattern are all immediates; a run-time pass loop cost ~4 issue slots per sample)
-    fft_pass<LOG2N, WIN, 0>(a, buf, tid, frame0);
-    fft_pass<LOG2N, WIN, 1>(a, buf, tid, frame0);
-    if (P::PASSES == 3) fft_pass<LOG2N, WIN, 2>(a, buf, tid, frame0);
 
     // ---------------- last pass: radix-F combine + untangle + mirror + pack
     BinOut out;
@@ -442,6 +464,78 @@ __global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS, (LOG2N == 15) ? 1 : F
         const int fr = tid >> 1;
         const int k = (tid & 1) ? (P::L / 2) : 0;
         if (frame0 + fr < a.batch) item(fr, k, __ldg(a.twn + k));
+    }
+}
+
+template <int LOG2N, bool WIN, int QMODE, int OUT>
+__global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS, (LOG2N == 15) ? 1 : FRA_K2_MINBLOCKS) k2_fft(K2Args a)
+{
+    using P = FftPlan<LOG2N>;
+    FRA_DYN_SMEM(smem_raw);
+    float2 *buf = reinterpret_cast<float2 *>(smem_raw);
+    const int tid = threadIdx.x;
+    const int frame0 = blockIdx.x * P::FPC;
+#ifdef FRA_TIMELINE
+    timeline_mark(2, a.tl_step);
+#endif
+    // ---------------------------------------------- radix-16 Stockham passes
+    // (compile-time pass index: twiddle strides, swizzled offsets and the pass-specific store
+    // pattern are all immediates; a run-time pass loop cost ~4 issue slots per sample)
+    fft_pass<LOG2N, WIN, 0>(a, buf, tid, frame0);
+    fft_pass<LOG2N, WIN, 1>(a, buf, tid, frame0);
+    if (P::PASSES == 3) fft_pass<LOG2N, WIN, 2>(a, buf, tid, frame0);
+    fft_last_pass<LOG2N, QMODE, OUT>(a, buf, tid, frame0);
+#ifdef FRA_TIMELINE
+    timeline_mark(3, a.tl_step);
+#endif
+}
+
+// The same for N = 16384 with PERSISTENT CTAs (two per SM) and the int16 frame staged by the TMA
+// engine: one thread issues ONE 32 KiB cp.async.bulk (SASS UBLKCP) per frame into a raw buffer
+// behind the FFT buffer, completing on an mbarrier, and it does so for frame i + 1 as soon as
+// pass 0 of frame i has consumed the buffer - so the DRAM latency of a frame's input is hidden
+// behind the three remaining passes of the frame before it, no thread spends an issue slot or a
+// register on global loads of samples, and pass 0 reads shared memory at unit stride.
+// (With per-thread loads 16 warps per SM could not cover that latency: long_scoreboard was the
+// first stall reason of k2_fft, profiles/r02_k2_fft_65536ch.txt.)
+constexpr int kStagedLog2N = 14;
+constexpr int kStagedRawBytes = FftPlan<kStagedLog2N>::M * 4;                       // the int16 frame: 32 KiB
+constexpr int kStagedSmemBytes = FftPlan<kStagedLog2N>::SMEM_BYTES + kStagedRawBytes + 16;
+
+template <bool WIN, int QMODE, int OUT>
+__global__ void __launch_bounds__(FftPlan<kStagedLog2N>::THREADS, FRA_K2_MINBLOCKS) k2_fft_staged(K2Args a)
+{
+    using P = FftPlan<kStagedLog2N>;
+    FRA_DYN_SMEM(smem_raw);
+    float2 *buf = reinterpret_cast<float2 *>(smem_raw);
+    uint2 *raw = reinterpret_cast<uint2 *>(smem_raw + P::SMEM_BYTES);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + P::SMEM_BYTES + kStagedRawBytes);
+    const int tid = threadIdx.x;
+#ifdef FRA_TIMELINE
+    timeline_mark(2, a.tl_step);
+#endif
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    unsigned phase = 0;
+    int frame = blockIdx.x;
+    if (tid == 0 && frame < a.batch) {
+        mbar_expect_tx(bar, (unsigned)kStagedRawBytes);
+        bulk_g2s(raw, a.in + (size_t)frame * P::M, (unsigned)kStagedRawBytes, bar);
+    }
+    for (; frame < a.batch; frame += (int)gridDim.x) {
+        mbar_wait(bar, phase);                               // this frame's samples have landed
+        phase ^= 1u;
+        fft_pass<kStagedLog2N, WIN, 0>(a, buf, tid, frame, raw);      // ends with a barrier: everyone has read `raw`
+        const int next = frame + (int)gridDim.x;
+        if (tid == 0 && next < a.batch) {
+            fence_proxy_async();                             // the generic-proxy reads above before the bulk copy's writes
+            mbar_expect_tx(bar, (unsigned)kStagedRawBytes);
+            bulk_g2s(raw, a.in + (size_t)next * P::M, (unsigned)kStagedRawBytes, bar);
+        }
+        fft_pass<kStagedLog2N, WIN, 1>(a, buf, tid, frame);
+        fft_pass<kStagedLog2N, WIN, 2>(a, buf, tid, frame);
+        fft_last_pass<kStagedLog2N, QMODE, OUT>(a, buf, tid, frame);
+        __syncthreads();                                     // the last pass has read `buf` before the next frame's pass 0 writes it
     }
 #ifdef FRA_TIMELINE
     timeline_mark(3, a.tl_step);

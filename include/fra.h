@@ -76,6 +76,9 @@ typedef enum fra_status {
 #define FRA_K1_NO_BIASED    0x80u    /* never use the all-biased biquad step (five FFMAs + one PRMT per stage);
                                         same results - for A/B timing and to test the general step with eligible coefficients */
 
+#define FRA_K2_NO_STAGED    0x100u   /* 16K frames: one frame per CTA with per-thread loads instead of persistent CTAs whose
+                                        frames arrive by one bulk copy each (cp.async.bulk); same results, for A/B timing */
+
 typedef struct fra_ctx fra_ctx;      /* opaque: ROM, two coefficient banks, IIR state, twiddles, one stream */
 
 /* Lifetime.  n_channels independent channels, fft_size in {1024,...,65536}

@@ -1,0 +1,109 @@
+"""Vectors obtained from the reference's VHDL TEXT (tests/golden/rtl_vectors.npz, produced in the
+build container by tests/golden/make_golden.py --rtl: the window, the biquad and both cascades
+parsed from /root/reference and executed with numeric_std semantics by tests/golden/vhdl_eval.py).
+
+They pin (i) the oracle - oracle/golden.py and oracle/golden.c must reproduce them bit for bit -
+and (ii), under -m gpu, the CUDA path itself through the C ABI.  The reference holds no vectors of
+its own for this path and cannot be simulated here (no ghdl / nvc / xsim): these are as close as the
+image gets to running it."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import cgolden as cg
+from oracle import golden as g
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CHAINS = ["chain_bank0_tone", "chain_bank0_full_2frames", "chain_bank1_full", "chain_bank1_extreme_gap"]
+
+
+@pytest.fixture(scope="module")
+def vec():
+    return np.load(os.path.join(ROOT, "tests", "golden", "rtl_vectors.npz"))
+
+
+def test_biquad_entity_vectors(vec):
+    """filter_iir_cust.vhd alone: ALPHA takes registers 0..4, BETA 6..10; i_valid gaps clear the history."""
+    for ft, off in (("alpha", 0), ("beta", 6)):
+        for case in range(3):
+            key = f"biquad_{ft}_{case}"
+            x, valid, coef, y = vec[key + "_x"], vec[key + "_valid"], vec[key + "_coef"], vec[key + "_y"]
+            exp = np.zeros_like(y)
+            i = 0
+            while i < len(x):
+                if not valid[i]:
+                    i += 1
+                    continue
+                j = i
+                while j < len(x) and valid[j]:
+                    j += 1
+                seg, _ = g.biquad(x[i:j][None], coef[off:off + 5])
+                exp[i:j] = seg[0]
+                i = j
+            assert np.array_equal(y[valid], exp[valid]), key
+            assert not y[~valid].any()                    # vs(0) of an idle stage is the sum of zero products
+
+
+def test_window_vectors_every_rom_address(vec, rom):
+    x, y = vec["window_x"], vec["window_y"]
+    assert len(x) == 16384
+    assert np.array_equal(g.window(x[None], rom)[0], y)
+    # the resize quirk is in there: x = c = -32768 -> 0
+    hit = (x == -32768) & (rom == -32768)
+    assert hit.sum() >= 40 and not y[hit].any()
+
+
+@pytest.mark.parametrize("key", CHAINS)
+def test_chain_vectors_numpy_and_c_oracle(vec, rom, key):
+    x, win, y, coef = vec[key + "_x"], vec[key + "_win"], vec[key + "_y"], vec[key + "_coef"]
+    gap = bool(vec[key + "_gap"][0])
+    mode = 0x00 if "bank0" in key else 0xA1
+    st_np = st_c = None
+    for f in range(x.shape[0]):
+        assert np.array_equal(g.window(x[f][None], rom)[0], win[f]), (key, f)
+        if gap:
+            st_np = st_c = None                           # the burst after a gap starts from zero history
+        c12 = g.BANK0_COEFF if mode == 0x00 else coef
+        y_np, st_np = g.iir12(win[f][None], c12, st_np)
+        assert np.array_equal(y_np[0], y[f]), (key, f, "numpy oracle")
+        y_c, st_c = cg.window_iir(x[f][None], rom, mode, g.BANK0_COEFF, coef, st_c)
+        assert np.array_equal(y_c[0], y[f]), (key, f, "C oracle")
+
+
+def test_bank0_constants_come_from_the_package(vec):
+    """the bank-0 chain was elaborated with filter_pkg.vhd's constants, not with ours"""
+    assert not vec["chain_bank0_tone_coef"].any()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", ["auto", "lane", "duo", "split", "stage"])
+@pytest.mark.parametrize("key", CHAINS)
+def test_cuda_path_reproduces_the_vhdl_vectors(vec, key, variant):
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.fail("-m gpu tests need a CUDA device; there is no CPU fallback")
+    from fpga_real_time_fft_analyzer_b200 import FraContext, _abi
+    flags = {"auto": 0, "lane": _abi.FRA_K1_FORCE_LANE, "duo": _abi.FRA_K1_FORCE_DUO,
+             "split": _abi.FRA_K1_FORCE_SPLIT, "stage": _abi.FRA_K1_FORCE_STAGE}[variant]
+    x, win, y, coef = vec[key + "_x"], vec[key + "_win"], vec[key + "_y"], vec[key + "_coef"]
+    gap = bool(vec[key + "_gap"][0])
+    c = 33                                               # the vector in channel 0, 17 and 32; noise elsewhere
+    rng = np.random.default_rng(1)
+    with FraContext(c, 16384, flags=flags) as ctx:
+        if "bank0" in key:
+            ctx.command(0x00)
+        else:
+            ctx.command(bytes([0xF1]) + coef.tobytes() + bytes([0xA1]))      # the 0xF1 byte protocol
+        for f in range(x.shape[0]):
+            batch = rng.integers(-32768, 32768, (c, 16384)).astype(np.int16)
+            batch[[0, 17, 32]] = x[f]
+            out = ctx.process(torch.from_numpy(batch).cuda(), continuous=(f > 0 and not gap), want=("filtered",))
+            got = out["filtered"].cpu().numpy()
+            for ch in (0, 17, 32):
+                assert np.array_equal(got[ch], y[f]), (key, variant, f, ch)
+        # the window alone (bypass, 0xB1): the FFT input stream is the windowed frame
+        ctx.command(0xB1)
+        batch = np.repeat(x[-1][None], c, axis=0)
+        got = ctx.process(torch.from_numpy(batch).cuda(), want=("filtered",))["filtered"].cpu().numpy()
+        assert np.array_equal(got[5], win[-1])
