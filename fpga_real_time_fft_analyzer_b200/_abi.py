@@ -35,7 +35,8 @@ FRA_K1_FORCE_STAGE = 0x10
 FRA_K1_FORCE_DUO = 0x20
 FRA_PIPELINE = 0x40
 FRA_K1_NO_BIASED = 0x80
-FRA_K2_NO_STAGED = 0x100
+FRA_K2_STAGED = 0x100
+FRA_FFT_FIXED16 = 0x200
 
 
 class FraOutputs(C.Structure):

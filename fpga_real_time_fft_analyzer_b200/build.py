@@ -8,7 +8,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(_HERE, "csrc", "fra_api.cu")
 OUT = os.path.join(_HERE, "libfra.so")
-DEPS = ["fra_api.cu", "fra_common.cuh", "k1_window_iir.cuh", "k1b_stream.cuh", "k2_fft.cuh", "hann_rom_q15.inc"]
+DEPS = ["fra_api.cu", "fra_common.cuh", "k1_window_iir.cuh", "k1b_stream.cuh", "k2_fft.cuh", "k2_fixed.cuh", "hann_rom_q15.inc"]
 
 
 def nvcc_path():

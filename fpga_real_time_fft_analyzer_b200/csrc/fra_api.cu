@@ -9,6 +9,7 @@
 #include "k1_window_iir.cuh"
 #include "k1b_stream.cuh"
 #include "k2_fft.cuh"
+#include "k2_fixed.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -67,6 +68,7 @@ struct fra_ctx {
     int16_t *d_state = nullptr;       // [C][6][4]
     int16_t *d_scratch = nullptr;     // [C][N] filter output when the caller does not ask for it
     float2 *d_tw1 = nullptr, *d_tw2 = nullptr, *d_twn = nullptr;
+    uint32_t *d_twfx = nullptr;       // FRA_FFT_FIXED16: W_N^t as packed Q1.15 pairs
     // 64K frames: W_65536^k and the scratch of the even/odd decomposition (k2_fft.cuh)
     float2 *d_twc = nullptr, *d_halves = nullptr;
     int16_t *d_split = nullptr;
@@ -203,10 +205,10 @@ int launch_k2_inst(fra_ctx *ctx, const K2Args &args, cudaStream_t st)
     // frames-only is the hot configuration and gets its own instantiation
     const bool frames_only = args.frames && !args.iq && !args.mag && !args.phase;
     if constexpr (LOG2N == kStagedLog2N) {
-        // 16K frames: persistent CTAs, each frame staged by one bulk copy (k2_fft.cuh).  The bulk copy needs a
-        // 16-byte aligned source; a pipelined context keeps the one-frame-per-CTA kernel, whose CTAs come and
-        // go and leave room for the window+IIR kernel's CTAs beside them.
-        const bool staged = !(ctx->flags & (FRA_K2_NO_STAGED | FRA_PIPELINE)) && (reinterpret_cast<uintptr_t>(args.in) % 16) == 0;
+        // 16K frames, on request (FRA_K2_STAGED): persistent CTAs, each frame staged by one bulk copy (k2_fft.cuh).
+        // Measured slower than the one-frame-per-CTA kernel (1.79 vs 1.62 ms per 65536 frames), so
+        // not the default.  The bulk copy needs a 16-byte aligned source.
+        const bool staged = (ctx->flags & FRA_K2_STAGED) && !(ctx->flags & FRA_PIPELINE) && (reinterpret_cast<uintptr_t>(args.in) % 16) == 0;
         if (staged && args.batch > 0) {
             auto sfn = frames_only ? k2_fft_staged<WIN, QMODE, 0> : k2_fft_staged<WIN, QMODE, 1>;
             FRA_SMEM(ctx, sfn, kStagedSmemBytes);
@@ -310,8 +312,28 @@ int launch_k2_64k(fra_ctx *ctx, const K2Args &args, bool win, int qmode, cudaStr
     return FRA_OK;
 }
 
+// FRA_FFT_FIXED16: the 16-bit scaled, truncating radix-2^2 pipeline (k2_fixed.cuh), one frame per CTA
+int launch_k2_fixed(fra_ctx *ctx, const K2Args &args, bool win, cudaStream_t st)
+{
+    const int smem = 4 << ctx->log2n;
+    if (args.batch <= 0) return FRA_OK;
+    if (win) {
+        auto kfn = k2_fixed<true>;
+        FRA_SMEM(ctx, kfn, smem);
+        FRA_LAUNCH(kfn, dim3(args.batch), dim3(kFixedThreads), (size_t)smem, st, args, (const uint32_t *)ctx->d_twfx, ctx->log2n);
+    } else {
+        auto kfn = k2_fixed<false>;
+        FRA_SMEM(ctx, kfn, smem);
+        FRA_LAUNCH(kfn, dim3(args.batch), dim3(kFixedThreads), (size_t)smem, st, args, (const uint32_t *)ctx->d_twfx, ctx->log2n);
+    }
+    FRA_TRY(ctx, cudaGetLastError());
+    ctx->last_kernels++;
+    return FRA_OK;
+}
+
 int launch_k2(fra_ctx *ctx, const K2Args &args, bool win, int qmode, cudaStream_t st)
 {
+    if (ctx->flags & FRA_FFT_FIXED16) return launch_k2_fixed(ctx, args, win, st);
     switch (ctx->log2n) {
     case 10: return launch_k2_n<10>(ctx, args, win, qmode, st);
     case 11: return launch_k2_n<11>(ctx, args, win, qmode, st);
@@ -410,7 +432,8 @@ int process_range(fra_ctx *ctx, const int16_t *d_in, int c0, int nch, int contin
             const int block = biased ? kLaneBiasedBlock : kLaneBlock;
             const int grid = (nch + block - 1) / block;
             auto kfn = biased ? (b1z ? k1_lane_biased<true> : k1_lane_biased<false>) : (b1z ? k1_lane<true> : k1_lane<false>);
-            FRA_LAUNCH(kfn, dim3(grid), dim3(block), (size_t)0, st, k1);
+            if (biased) FRA_SMEM(ctx, kfn, kLaneBiasedSmem);
+            FRA_LAUNCH(kfn, dim3(grid), dim3(block), (size_t)(biased ? kLaneBiasedSmem : 0), st, k1);
         }
         FRA_TRY(ctx, cudaGetLastError());
         if (ctx->profiling) {
@@ -556,6 +579,7 @@ int fra_create(fra_ctx **out, int device, int n_channels, int fft_size, unsigned
     while ((1 << log2n) < fft_size) ++log2n;
     if ((1 << log2n) != fft_size) return FRA_ERR_INVALID;
     if (log2n < 10 || log2n > 16) return FRA_ERR_UNSUPPORTED;
+    if ((flags & FRA_FFT_FIXED16) && log2n > 15) return FRA_ERR_UNSUPPORTED;      // the frame must fit one SM's shared memory
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return FRA_ERR_NO_DEVICE;
     if (device < 0 || device >= count) return FRA_ERR_INVALID;
@@ -624,6 +648,19 @@ int fra_create(fra_ctx **out, int device, int n_channels, int fft_size, unsigned
         cudaMemcpy(ctx->d_twn, twn.data(), twn.size() * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemset(ctx->d_state, 0, (size_t)n_channels * 24 * sizeof(int16_t)) != cudaSuccess)
         return bail(FRA_ERR_CUDA);
+    if (flags & FRA_FFT_FIXED16) {
+        // phase factors of the fixed-point mode: round(cos, -sin * 2^15) clipped to 32767 (xfft_0.xci:19, 16 bits)
+        std::vector<uint32_t> twfx(n);
+        for (size_t t = 0; t < n; ++t) {
+            const double a = two_pi * (double)t / (double)n;
+            const long wr = std::min(32767L, std::max(-32767L, std::lrint(std::cos(a) * 32768.0)));
+            const long wi = std::min(32767L, std::max(-32767L, std::lrint(-std::sin(a) * 32768.0)));
+            twfx[t] = ((uint32_t)wr & 0xFFFFu) | ((uint32_t)wi << 16);
+        }
+        if (cudaMalloc((void **)&ctx->d_twfx, n * sizeof(uint32_t)) != cudaSuccess) return bail(FRA_ERR_NOMEM);
+        if (cudaMemcpy(ctx->d_twfx, twfx.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess)
+            return bail(FRA_ERR_CUDA);
+    }
     // Work buffers are sized here, not in the first fra_process call: the filter-output scratch
     // (two of them in pipelined mode) and, for 64K frames, the even/odd split and its fp32 halves.
     {
@@ -655,7 +692,7 @@ int fra_destroy(fra_ctx *ctx)
         if (ps) { cudaStreamSynchronize(ps); cudaStreamDestroy(ps); }
     for (cudaEvent_t pe : {ctx->pipe_in, ctx->pipe_go, ctx->pipe_k1_done[0], ctx->pipe_k1_done[1], ctx->pipe_k2_done[0], ctx->pipe_k2_done[1]})
         if (pe) cudaEventDestroy(pe);
-    void *bufs[] = {ctx->d_rom32, ctx->d_rom2x, ctx->d_state, ctx->d_scratch, ctx->d_tw1, ctx->d_tw2, ctx->d_twn, ctx->d_in, ctx->d_twc, ctx->d_halves, ctx->d_split,
+    void *bufs[] = {ctx->d_rom32, ctx->d_rom2x, ctx->d_twfx, ctx->d_state, ctx->d_scratch, ctx->d_tw1, ctx->d_tw2, ctx->d_twn, ctx->d_in, ctx->d_twc, ctx->d_halves, ctx->d_split,
                     ctx->d_frames, ctx->d_filtered_out, ctx->d_iq, ctx->d_mag, ctx->d_phase, ctx->d_entry,
                     ctx->d_exit, ctx->d_counts, ctx->d_ends, ctx->d_aggr, ctx->d_mats};
     for (void *p : bufs)
@@ -795,6 +832,7 @@ int fra_process(fra_ctx *ctx, const int16_t *d_in, int continuous, int log2_scal
     if (!ctx || !d_in || !out) return FRA_ERR_INVALID;
     if (log2_scale == FRA_SCALE_DEFAULT) log2_scale = -ctx->log2n;
     if (log2_scale < -40 || log2_scale > 16) return FRA_ERR_INVALID;
+    if ((ctx->flags & FRA_FFT_FIXED16) && log2_scale != -ctx->log2n) return FRA_ERR_INVALID;   // the fixed pipeline's schedule is 1/N
     FRA_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;      // NULL = the legacy default stream
     const bool iir = (ctx->mode == FRA_MODE_BANK0 || ctx->mode == FRA_MODE_BANK1);
@@ -899,6 +937,7 @@ int fra_process_host_async(fra_ctx *ctx, const int16_t *h_in, int continuous, in
     if (!ctx || !h_in || !h_out || !ticket) return FRA_ERR_INVALID;
     if (log2_scale == FRA_SCALE_DEFAULT) log2_scale = -ctx->log2n;
     if (log2_scale < -40 || log2_scale > 16) return FRA_ERR_INVALID;
+    if ((ctx->flags & FRA_FFT_FIXED16) && log2_scale != -ctx->log2n) return FRA_ERR_INVALID;
     FRA_TRY(ctx, cudaSetDevice(ctx->device));
     FRA_TRY(ctx, pipe_host_join(ctx));                 // may launch the held-back FFT: after the device is current
     const size_t C = (size_t)ctx->channels, n = (size_t)ctx->n;

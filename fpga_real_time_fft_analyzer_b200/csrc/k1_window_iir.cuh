@@ -124,6 +124,10 @@ __global__ void __launch_bounds__(kLaneBlock) k1_lane(K1Args a)
     }
 }
 
+// byte offset of 16-byte piece `piece` of 128-byte line `row` in a staged [row][8 pieces] tile: the piece index is
+// XOR-swizzled with (row & 7), so line-wise access (eight lanes per row) and lane-per-row access are both conflict-free
+FRA_DEV int duo_swz(int row, int piece) { return row * 128 + ((piece ^ (row & 7)) << 4); }
+
 // ------------------------------------------------------------- k1_lane_biased
 // The lane-per-channel kernel on the all-biased step (fra_common.cuh: biquad_step_biased): every
 // value that moves between the window, the six stages and the history registers is the PRMT
@@ -219,19 +223,35 @@ FRA_DEV void lane_trip16(const K1Args &a, size_t c, const float (&u)[16], StageS
     carry[0] = acc[13]; carry[1] = acc[14]; carry[2] = acc[15];
 }
 
-// Four warps per CTA: a CTA's warps go to the four schedulers of its SM one each (warp id mod 4), so
-// the channels spread evenly over the 592 schedulers by construction.  (With one-warp CTAs the SM's
-// instruction rate stopped rising at ~1.9 per cycle however many CTAs were resident - 16384 channels:
-// 1.76, 65536: 1.9, profiles/r02_k1_lane_16384ch.txt.)
+// Four independent warps per CTA (no CTA-wide barrier), one lane per channel, and global memory touched in
+// whole 128-byte lines only, like k1_duo: a chunk of 64 samples of one channel IS one line, eight lanes move
+// it (cp.async 16 B in, STG.128 out), 32 lines = one 4 KiB buffer per warp, piece index XOR-swizzled with
+// (row & 7) so that both the line-wise and the lane-per-channel side are conflict-free.  (The first version
+// had every lane fetch its own 32 bytes per 16 samples: one sector per lane and request, DRAM pages opened
+// for 32 bytes each - the SM's instruction rate stopped rising at ~1.9 per cycle however many warps were
+// resident, profiles/r02_k1_lane_16384ch.txt.)  Outputs are written IN PLACE into the buffer the samples came
+// from (a lane only ever touches its own row there), and a chunk's lines are stored one 16-sample trip into
+// the next chunk, when the cascade's five-sample lag has delivered its last samples; the buffer is then
+// refilled with the chunk after next.  Two buffers per warp: 8.5 KiB, 34 KiB per CTA.
 constexpr int kLaneBiasedBlock = 128;
+constexpr int kLaneChunk = 64;                                  // samples per staged line
+constexpr int kLaneBufBytes = 32 * 128;                         // one chunk of 32 channels
+constexpr int kLaneWarpBytes = 2 * kLaneBufBytes + 2 * kLaneChunk * 4;      // two line buffers + two ROM slices
+constexpr int kLaneBiasedSmem = (kLaneBiasedBlock / 32) * kLaneWarpBytes;
 
 template <bool B1Z>
 __global__ void __launch_bounds__(kLaneBiasedBlock) k1_lane_biased(K1Args a)
 {
-    const int c_raw = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = c_raw < a.channels;
-    const size_t c = (size_t)(live ? c_raw : a.channels - 1);     // inactive lanes shadow the last channel (no stores)
+    FRA_DYN_SMEM(smem_raw);
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const int c0 = (blockIdx.x * (kLaneBiasedBlock / 32) + wrp) * 32;
+    if (c0 >= a.channels) return;                                  // warp-uniform; no CTA-wide barrier below
+    const bool live = c0 + lane < a.channels;
+    const size_t c = (size_t)(live ? c0 + lane : a.channels - 1); // inactive lanes shadow the last channel (no stores)
     const unsigned exp23 = a.coef.set[0].exp23;
+    unsigned char *lines = smem_raw + wrp * kLaneWarpBytes;        // [2][32 rows][8 pieces of 16 B]
+    int *roms = reinterpret_cast<int *>(lines + 2 * kLaneBufBytes);      // [2][64] doubled ROM entries
+    const int n_chunks = a.n / kLaneChunk;
 
     StageStateB st[kStages];
     float pipe[kStages], carry[3] = {0.0f, 0.0f, 0.0f};
@@ -241,28 +261,43 @@ __global__ void __launch_bounds__(kLaneBiasedBlock) k1_lane_biased(K1Args a)
         pipe[s] = kBias16;
     }
 
-    const int16_t *src = a.in + c * a.n;
-    int16_t *dst = a.out + c * a.n;
-
-    __shared__ uint4 stage_x[2][2][kLaneBiasedBlock];          // [buffer][half][thread]: 16 samples per lane
-    __shared__ int4 stage_rom[kLaneBiasedBlock / 32][2][4];    // [warp][buffer][4 x 4 doubled ROM entries]: the warps of a CTA drift apart
-    const int lane = threadIdx.x & 31, tix = threadIdx.x, wrp = threadIdx.x >> 5;
-    auto request = [&](int n0, int b) {
-        cp_async16(&stage_x[b][0][tix], src + n0);
-        cp_async16(&stage_x[b][1][tix], src + n0 + 8);
-        if (lane < 4) cp_async16(&stage_rom[wrp][b][lane], a.rom2x + ((n0 + 4 * lane) & (kWindowLen - 1)));
+    // chunk t -> buffer t & 1, whole lines: eight lanes per channel row, four rows per instruction
+    auto request = [&](int t) {
+        unsigned char *dst = lines + (t & 1) * kLaneBufBytes;
+        const int p = lane & 7;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = 4 * i + (lane >> 3);
+            const int ch = min(c0 + r, a.channels - 1);                       // rows past the end read valid memory
+            cp_async16(dst + duo_swz(r, p), a.in + (size_t)ch * a.n + (size_t)t * kLaneChunk + 8 * p);
+        }
+        if (lane < 16)
+            cp_async16(roms + (t & 1) * kLaneChunk + 4 * lane, a.rom2x + (((t * kLaneChunk) & (kWindowLen - 1)) + 4 * lane));
         cp_async_commit();
     };
-    // samples [n0, n0 + 16) of this lane's channel -> window -> biased floats
-    auto fetch = [&](int n0, int b, float (&u)[16]) {
-        if (n0 + 16 < a.n) request(n0 + 16, b ^ 1);
-        else cp_async_commit();
-        cp_async_wait<1>();
-        __syncwarp();                                 // the ROM words were copied by lanes 0..3
-        const uint4 xa = stage_x[b][0][tix], xb = stage_x[b][1][tix];
-        const int4 r0 = stage_rom[wrp][b][0], r1 = stage_rom[wrp][b][1], r2 = stage_rom[wrp][b][2], r3 = stage_rom[wrp][b][3];
+    // the finished chunk t: buffer -> global memory, whole lines
+    auto store_lines = [&](int t) {
+        const unsigned char *src = lines + (t & 1) * kLaneBufBytes;
+        const int p = lane & 7;
+        uint4 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const uint4 *>(src + duo_swz(4 * i + (lane >> 3), p));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int ch = c0 + 4 * i + (lane >> 3);
+            if (ch < a.channels) stg128(a.out + (size_t)ch * a.n + (size_t)t * kLaneChunk + 8 * p, v[i]);
+        }
+    };
+    // samples [16 g, 16 g + 16) of this lane's channel (trip g of the frame) -> window -> biased floats
+    auto fetch = [&](int g, float (&u)[16]) {
+        const int t = g >> 2, j = g & 3;
+        const unsigned char *buf = lines + (t & 1) * kLaneBufBytes;
+        const uint4 xa = *reinterpret_cast<const uint4 *>(buf + duo_swz(lane, 2 * j));
+        const uint4 xb = *reinterpret_cast<const uint4 *>(buf + duo_swz(lane, 2 * j + 1));
+        const int4 *rom = reinterpret_cast<const int4 *>(roms + (t & 1) * kLaneChunk + 16 * j);
+        const int4 r0 = rom[0], r1 = rom[1], r2 = rom[2], r3 = rom[3];       // same address in every lane: broadcast
         float ua[8], ub[8];
-        if (rom_quirk_range(n0 & (kWindowLen - 1), 16)) {      // warp-uniform
+        if (rom_quirk_range((16 * g) & (kWindowLen - 1), 16)) {               // warp-uniform
             window8_biased<true>(xa, r0, r1, exp23, ua);
             window8_biased<true>(xb, r2, r3, exp23, ub);
         } else {
@@ -270,26 +305,45 @@ __global__ void __launch_bounds__(kLaneBiasedBlock) k1_lane_biased(K1Args a)
             window8_biased<false>(xb, r2, r3, exp23, ub);
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { u[j] = ua[j]; u[8 + j] = ub[j]; }
-        __syncwarp();                                 // everyone has read buffer b before it is refilled
+        for (int jj = 0; jj < 8; ++jj) { u[jj] = ua[jj]; u[8 + jj] = ub[jj]; }
+    };
+    // the two finished 8-sample groups of trip g, in place: samples [16 g - 8, 16 g) and [16 g, 16 g + 8)
+    auto put = [&](int g, uint4 ga, uint4 gb) {
+        const int t = g >> 2, j = g & 3;
+        unsigned char *buf = lines + (t & 1) * kLaneBufBytes;
+        *reinterpret_cast<uint4 *>(buf + duo_swz(lane, 2 * j)) = gb;
+        if (j > 0) *reinterpret_cast<uint4 *>(buf + duo_swz(lane, 2 * j - 1)) = ga;
+        else if (t > 0) *reinterpret_cast<uint4 *>(lines + ((t - 1) & 1) * kLaneBufBytes + duo_swz(lane, 7)) = ga;
     };
 
-    request(0, 0);
+    request(0);
+    cp_async_wait<0>();
+    __syncwarp();                                     // every line was copied by eight different lanes
     uint4 ga, gb;
     {
         float u[16];
-        fetch(0, 0, u);
+        fetch(0, u);
         lane_trip16<B1Z, true>(a, c, u, st, pipe, carry, ga, gb);
-        if (live) stg128(dst, gb);                     // samples 0..7; the group before them does not exist
+        put(0, ga, gb);
+        if (n_chunks > 1) request(1);
     }
+    const int n_trips = a.n / 16;
 #pragma unroll 1
-    for (int n0 = 16, it = 1; n0 < a.n; n0 += 16, ++it) {
+    for (int g = 1; g < n_trips; ++g) {
+        const int t = g >> 2;
+        if ((g & 3) == 0) {
+            cp_async_wait<0>();                       // chunk t (requested three trips ago) has landed
+            __syncwarp();
+        }
         float u[16];
-        fetch(n0, it & 1, u);
+        fetch(g, u);
         lane_trip16<B1Z, false>(a, c, u, st, pipe, carry, ga, gb);
-        if (live) {
-            stg128(dst + n0 - 8, ga);
-            stg128(dst + n0, gb);
+        put(g, ga, gb);
+        if ((g & 3) == 0) {
+            __syncwarp();                             // chunk t - 1 is complete in its buffer
+            store_lines(t - 1);
+            __syncwarp();                             // ... and read out, before the copy engine refills it
+            if (t + 1 < n_chunks) request(t + 1);
         }
     }
     // drain: iterations n .. n + 4 push samples n - 5 .. n - 1 through the remaining stages.  Stage s saw
@@ -302,13 +356,13 @@ __global__ void __launch_bounds__(kLaneBiasedBlock) k1_lane_biased(K1Args a)
         tail[j] = lane_skewed_iteration<B1Z>(kBias16, a.coef, st, pipe);
         if (live) store_state_biased(a.state, c, j + 1, st[j + 1]);
     }
-    if (live) {
-        ga.x = pack16_acc(carry[0], carry[1]);
-        ga.y = pack16_acc(carry[2], tail[0]);
-        ga.z = pack16_acc(tail[1], tail[2]);
-        ga.w = pack16_acc(tail[3], tail[4]);
-        stg128(dst + a.n - 8, ga);
-    }
+    ga.x = pack16_acc(carry[0], carry[1]);
+    ga.y = pack16_acc(carry[2], tail[0]);
+    ga.z = pack16_acc(tail[1], tail[2]);
+    ga.w = pack16_acc(tail[3], tail[4]);
+    *reinterpret_cast<uint4 *>(lines + ((n_chunks - 1) & 1) * kLaneBufBytes + duo_swz(lane, 7)) = ga;
+    __syncwarp();
+    store_lines(n_chunks - 1);
 }
 
 // ----------------------------------------------------------------- k1_split
@@ -809,7 +863,6 @@ constexpr int kDuoSmemBytes = kDuoRomOff + 2 * kDuoRomBytes;                // 7
 // occupies (measured: 0.273 -> 0.260 ms per step in the pipeline's good mode).
 constexpr int kDuoSmemRequest = 96 * 1024;
 
-FRA_DEV int duo_swz(int row, int piece) { return row * 128 + ((piece ^ (row & 7)) << 4); }
 
 // Every stage warp runs the SAME branch-free straight-line chunk body: the last pair also
 // leaves its output as a float tile, and the writer warp (on the scheduler the pair warps do

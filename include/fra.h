@@ -76,8 +76,15 @@ typedef enum fra_status {
 #define FRA_K1_NO_BIASED    0x80u    /* never use the all-biased biquad step (five FFMAs + one PRMT per stage);
                                         same results - for A/B timing and to test the general step with eligible coefficients */
 
-#define FRA_K2_NO_STAGED    0x100u   /* 16K frames: one frame per CTA with per-thread loads instead of persistent CTAs whose
-                                        frames arrive by one bulk copy each (cp.async.bulk); same results, for A/B timing */
+#define FRA_K2_STAGED       0x100u   /* 16K frames: persistent FFT CTAs whose frames arrive by one bulk copy each (cp.async.bulk on an
+                                        mbarrier) instead of one frame per CTA with per-thread loads; same results, measured
+                                        slower on B200, kept for A/B timing */
+#define FRA_FFT_FIXED16     0x200u   /* the FFT as the 16-bit fixed-point, scaled, truncating radix-2^2 pipeline the Xilinx core is
+                                        configured to be (IP/xfft_0/xfft_0.xci:12-27: 16-bit data and phase factors, scaled 1/N,
+                                        truncation, natural order) instead of fp32: the spectrum carries FPGA-like quantisation
+                                        noise.  Arithmetic defined in csrc/k2_fixed.cuh / oracle/fixed_fft.py; bit-level parity with
+                                        the proprietary core is UNPINNED.  fft_size <= 32768, log2_scale must be the default (1/N);
+                                        d_iq receives the int16 bins times N as floats. */
 
 typedef struct fra_ctx fra_ctx;      /* opaque: ROM, two coefficient banks, IIR state, twiddles, one stream */
 

@@ -175,6 +175,7 @@ static inline float __fadd_rd(float a, float b) { return cusim_add_mode(a, b, FE
 static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 static inline float __fsqrt_rn(float a) { return std::sqrt(a); }
+static inline unsigned __brev(unsigned v) { unsigned r = 0; for (int i = 0; i < 32; ++i) r |= ((v >> i) & 1u) << (31 - i); return r; }
 static inline unsigned __float_as_uint(float f) { return cusim::to_bits(f) & 0xffffffffu; }
 static inline int __float_as_int(float f) { return (int)__float_as_uint(f); }
 static inline float __uint_as_float(unsigned u) { return cusim::from_bits<float>(u); }

@@ -379,3 +379,42 @@ def test_all_biased_step_at_the_edge_of_its_condition(flags, rom):
                 assert np.array_equal(f.get_state(), st)
             finally:
                 f.close()
+
+
+@pytest.mark.parametrize("n", [1024, 2048, 16384])
+def test_fixed_point_fft_mode_bit_exact_vs_integer_oracle(n, rom):
+    """FRA_FFT_FIXED16: the 16-bit scaled, truncating radix-2^2 pipeline (what xfft_0.xci configures;
+    parity with the proprietary core unpinned) equals oracle/fixed_fft.py bit for bit, and stays
+    within a few LSB of the float64 FFT / N."""
+    from oracle.fixed_fft import fixed_fft
+    rng = np.random.default_rng(n)
+    c = 3
+    x = g.tone_noise(range(c), n=n, seed=3)
+    x[2] = rng.integers(-32768, 32768, n)
+    f = EmulFra(c, n, _abi.FRA_FFT_FIXED16)
+    try:
+        f.command(bytes([0x00]))
+        out = f.process(x, want=("filtered", "frames", "iq", "mag"))
+        y, _ = cg.window_iir(x, rom, 0x00, g.BANK0_COEFF, B1)
+        assert np.array_equal(out["filtered"], y)
+        re, im = fixed_fft(y)
+        gre, gim, gmag = g.decode_frame(out["frames"])
+        assert np.array_equal(gre, re) and np.array_equal(gim, im)
+        assert np.array_equal(out["mag"].view(np.uint32), gmag.astype(np.float32).view(np.uint32))
+        assert np.array_equal(out["iq"][..., 0], re.astype(np.float32) * n)
+        ref = np.fft.fft(y.astype(np.float64), axis=-1) / n
+        assert np.abs((re + 1j * im) - ref).max() < 8.0
+        # bypass: the window fused into the load
+        f.command(bytes([0xB1]))
+        out = f.process(x, want=("frames",))
+        re, im = fixed_fft(g.window(x, rom))
+        gre, gim, _ = g.decode_frame(out["frames"])
+        assert np.array_equal(gre, re) and np.array_equal(gim, im)
+        # only the core's 1/N schedule exists in this mode
+        import ctypes as C2
+        o = _abi.FraOutputs(None, out["frames"].ctypes.data, None, None, None)
+        assert f.L.fra_process(f.h, x.ctypes.data, 0, -3, C2.byref(o), None) == _abi.FRA_ERR_INVALID
+    finally:
+        f.close()
+    h = C.c_void_p()
+    assert lib().fra_create(C.byref(h), 0, 1, 65536, _abi.FRA_FFT_FIXED16) == _abi.FRA_ERR_UNSUPPORTED

@@ -529,3 +529,44 @@ def test_all_biased_step_at_the_edge_of_its_condition(fra, rom, variant):
                 assert np.array_equal(ctx.process(dev(xa), continuous=True, want=("filtered",))["filtered"].cpu().numpy(), ya)
                 assert np.array_equal(ctx.process(dev(xb), continuous=True, want=("filtered",))["filtered"].cpu().numpy(), yb)
                 assert np.array_equal(ctx.get_state().cpu().numpy(), st)
+
+
+@pytest.mark.parametrize("n", [1024, 4096, 16384, 32768])
+def test_fixed_point_fft_mode(fra, rom, n):
+    """FRA_FFT_FIXED16: 16-bit data, 16-bit phase factors, scaled 1/N, truncation - the
+    configuration of xfft_0.xci - as a radix-2^2 integer pipeline.  Bit-exact against the integer oracle
+    (oracle/fixed_fft.py); within the quantisation noise expected of such a pipeline against the float64
+    FFT (a few LSB peak, ~1 LSB rms).  Bit-level parity with the proprietary Xilinx core: UNPINNED."""
+    from oracle.fixed_fft import fixed_fft
+    rng = np.random.default_rng(n)
+    c = 37
+    x = g.tone_noise(range(c), n=n, seed=5)
+    x[-1] = rng.integers(-32768, 32768, n)
+    with fra.FraContext(c, n, flags=fra._abi.FRA_FFT_FIXED16) as ctx:
+        ctx.command(0x00)
+        out = {k: v.cpu().numpy() for k, v in ctx.process(dev(x), want=("filtered", "frames", "iq", "mag", "phase")).items()}
+        y, _ = cg.window_iir(x, rom, 0x00, g.BANK0_COEFF, B1)
+        assert np.array_equal(out["filtered"], y)
+        re, im = fixed_fft(y)
+        gre, gim, gmag = g.decode_frame(out["frames"])
+        assert np.array_equal(gre, re) and np.array_equal(gim, im)
+        assert np.array_equal(out["mag"].view(np.uint32), gmag.astype(np.float32).view(np.uint32))
+        assert np.abs(out["phase"] - np.arctan2(gim, gre)).max() < 2e-6
+        assert np.array_equal(out["iq"][..., 0], re.astype(np.float32) * n)
+        ref = np.fft.fft(y.astype(np.float64), axis=-1) / n
+        err = (re + 1j * im) - ref
+        assert np.abs(err).max() < 8.0 and np.sqrt((np.abs(err) ** 2).mean()) < 1.5
+        # the float path on the same input: its int16 bins agree with the fixed-point ones to the same few LSB
+        with fra.FraContext(c, n) as fl:
+            fl.command(0x00)
+            fre, fim, _ = g.decode_frame(fl.process(dev(x), want=("frames",))["frames"].cpu().numpy())
+        assert np.abs(fre.astype(int) - re).max() <= 8 and np.abs(fim.astype(int) - im).max() <= 8
+        ctx.command(0xB1)                                     # bypass: window fused into the load
+        o2 = ctx.process(dev(x), want=("frames",))["frames"].cpu().numpy()
+        re, im = fixed_fft(g.window(x, rom))
+        gre, gim, _ = g.decode_frame(o2)
+        assert np.array_equal(gre, re) and np.array_equal(gim, im)
+        with pytest.raises(fra.FraError):
+            ctx.process(dev(x), log2_scale=-3, want=("frames",))
+    with pytest.raises(fra.FraError):
+        fra.FraContext(1, 65536, flags=fra._abi.FRA_FFT_FIXED16)
