@@ -11,5 +11,6 @@ from ._abi import (FILTER_CUSTOM_CMD, FILTER_DEFAULT_CMD, FILTER_NONE_CMD, FILTE
 from ._lib import FraError
 from .context import FraContext
 from .receiver import GpuReceiver, frame_to_udp_payloads
+from .udp_emitter import UdpFrameSender
 
-__all__ = ["FraContext", "FraError", "GpuReceiver", "frame_to_udp_payloads", "filter_design", "_abi"]
+__all__ = ["FraContext", "FraError", "GpuReceiver", "UdpFrameSender", "frame_to_udp_payloads", "filter_design", "_abi"]

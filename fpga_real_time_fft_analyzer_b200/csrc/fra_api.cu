@@ -403,10 +403,10 @@ int process_range(fra_ctx *ctx, const int16_t *d_in, int c0, int nch, int contin
             // every operand biased, no FADD at all (fra_common.cuh: biquad_step_biased)
             biased = biased && biased_order_ok(sec.c[i][0], sec.c[i][1], sec.c[i][2], sec.c[i][3], sec.c[i][4]);
         }
+        bool alt = true;                                           // ALPHA, BETA, ALPHA, BETA, ALPHA, BETA
+        for (int i = 2; i < kStages; ++i) alt = alt && std::memcmp(sec.c[i], sec.c[i & 1], 5) == 0;
         if (variant == 3) {
             const int grid = (nch + 31) / 32;
-            bool alt = true;                                       // ALPHA, BETA, ALPHA, BETA, ALPHA, BETA
-            for (int i = 2; i < kStages; ++i) alt = alt && std::memcmp(sec.c[i], sec.c[i & 1], 5) == 0;
             void (*const table[12])(K1Args) = {
                 k1_duo<false, 0, false>, k1_duo<true, 0, false>, k1_duo<false, 1, false>, k1_duo<true, 1, false>,
                 k1_duo<false, 2, false>, k1_duo<true, 2, false>,
@@ -431,7 +431,9 @@ int process_range(fra_ctx *ctx, const int16_t *d_in, int c0, int nch, int contin
         } else {
             const int block = biased ? kLaneBiasedBlock : kLaneBlock;
             const int grid = (nch + block - 1) / block;
-            auto kfn = biased ? (b1z ? k1_lane_biased<true> : k1_lane_biased<false>) : (b1z ? k1_lane<true> : k1_lane<false>);
+            void (*const lane_table[4])(K1Args) = {k1_lane_biased<false, false>, k1_lane_biased<true, false>,
+                                                   k1_lane_biased<false, true>, k1_lane_biased<true, true>};
+            auto kfn = biased ? lane_table[(b1z ? 1 : 0) | (alt ? 2 : 0)] : (b1z ? k1_lane<true> : k1_lane<false>);
             if (biased) FRA_SMEM(ctx, kfn, kLaneBiasedSmem);
             FRA_LAUNCH(kfn, dim3(grid), dim3(block), (size_t)(biased ? kLaneBiasedSmem : 0), st, k1);
         }

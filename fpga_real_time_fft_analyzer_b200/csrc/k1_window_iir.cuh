@@ -182,14 +182,16 @@ FRA_DEV bool rom_quirk_range(int w0, int len)
 // one chain through all six stages (75 cycles per sample measured for the sample-major order; the
 // critical path here is one stage step).  Stages are visited last to first so that pipe[s - 1]
 // still holds the previous iteration's value.  Returns the last stage's accumulator (sample i - 5).
-template <bool B1Z>
+// ALT: the six stages use two alternating coefficient sets (the RTL's bank layout): a dozen values that
+// stay in uniform registers, instead of 36 of which most are re-read from the constant bank every trip
+template <bool B1Z, bool ALT>
 FRA_DEV float lane_skewed_iteration(float ux, const CascadeCoef &coef, StageStateB (&st)[kStages], float (&pipe)[kStages])
 {
     float acc = 0.0f;
 #pragma unroll
     for (int s = kStages - 1; s >= 0; --s) {
         const float in = (s == 0) ? ux : pipe[s - 1];
-        const float r = biquad_step_biased<B1Z>(in, coef.set[s], st[s], &pipe[s]);
+        const float r = biquad_step_biased<B1Z>(in, coef.set[ALT ? (s & 1) : s], st[s], &pipe[s]);
         if (s == kStages - 1) acc = r;
     }
     return acc;
@@ -202,7 +204,7 @@ constexpr int kLaneLag = kStages - 1;      // the last stage emits sample i - 5 
 // guard anywhere.  The accumulators of samples i0 - 5 .. i0 + 10 come out; with the three carried
 // from the trip before (i0 - 8 .. i0 - 6) they complete the 16-byte groups [i0 - 8, i0) and
 // [i0, i0 + 8); the last three are carried on.
-template <bool B1Z, bool FIRST>
+template <bool B1Z, bool ALT, bool FIRST>
 FRA_DEV void lane_trip16(const K1Args &a, size_t c, const float (&u)[16], StageStateB (&st)[kStages], float (&pipe)[kStages],
                          float (&carry)[3], uint4 &ga, uint4 &gb)
 {
@@ -210,7 +212,7 @@ FRA_DEV void lane_trip16(const K1Args &a, size_t c, const float (&u)[16], StageS
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
         if (FIRST && j < kStages) st[j] = load_state_biased(a.state, c, j, a.continuous != 0);
-        acc[j] = lane_skewed_iteration<B1Z>(u[j], a.coef, st, pipe);
+        acc[j] = lane_skewed_iteration<B1Z, ALT>(u[j], a.coef, st, pipe);
     }
     ga.x = pack16_acc(carry[0], carry[1]);
     ga.y = pack16_acc(carry[2], acc[0]);
@@ -239,7 +241,7 @@ constexpr int kLaneBufBytes = 32 * 128;                         // one chunk of 
 constexpr int kLaneWarpBytes = 2 * kLaneBufBytes + 2 * kLaneChunk * 4;      // two line buffers + two ROM slices
 constexpr int kLaneBiasedSmem = (kLaneBiasedBlock / 32) * kLaneWarpBytes;
 
-template <bool B1Z>
+template <bool B1Z, bool ALT>
 __global__ void __launch_bounds__(kLaneBiasedBlock) k1_lane_biased(K1Args a)
 {
     FRA_DYN_SMEM(smem_raw);
@@ -323,7 +325,7 @@ __global__ void __launch_bounds__(kLaneBiasedBlock) k1_lane_biased(K1Args a)
     {
         float u[16];
         fetch(0, u);
-        lane_trip16<B1Z, true>(a, c, u, st, pipe, carry, ga, gb);
+        lane_trip16<B1Z, ALT, true>(a, c, u, st, pipe, carry, ga, gb);
         put(0, ga, gb);
         if (n_chunks > 1) request(1);
     }
@@ -337,7 +339,7 @@ __global__ void __launch_bounds__(kLaneBiasedBlock) k1_lane_biased(K1Args a)
         }
         float u[16];
         fetch(g, u);
-        lane_trip16<B1Z, false>(a, c, u, st, pipe, carry, ga, gb);
+        lane_trip16<B1Z, ALT, false>(a, c, u, st, pipe, carry, ga, gb);
         put(g, ga, gb);
         if ((g & 3) == 0) {
             __syncwarp();                             // chunk t - 1 is complete in its buffer
@@ -353,7 +355,7 @@ __global__ void __launch_bounds__(kLaneBiasedBlock) k1_lane_biased(K1Args a)
     float tail[kLaneLag];
 #pragma unroll
     for (int j = 0; j < kLaneLag; ++j) {
-        tail[j] = lane_skewed_iteration<B1Z>(kBias16, a.coef, st, pipe);
+        tail[j] = lane_skewed_iteration<B1Z, ALT>(kBias16, a.coef, st, pipe);
         if (live) store_state_biased(a.state, c, j + 1, st[j + 1]);
     }
     ga.x = pack16_acc(carry[0], carry[1]);

@@ -28,7 +28,8 @@ class GpuReceiver:
     numpy array / CPU torch tensor (e2e path) or a CUDA torch tensor (resident path)."""
 
     def __init__(self, source, channels: int = 1, fft_size: int = SAMPLES_PER_FRAME, device: int = 0,
-                 continuous: bool = True, want=("frames",), flags: int = 0):
+                 continuous: bool = True, want=("frames",), flags: int = 0, free_running: bool = False,
+                 max_backlog: int = 10):
         self.ctx = FraContext(channels, fft_size, device, flags)      # raises like UartReceiver's open (GUI:482-484)
         self.source = source
         self.channels, self.fft_size = channels, fft_size
@@ -40,6 +41,12 @@ class GpuReceiver:
         self._seen_request = 0
         self._first = True
         self.last_reset_time = 0.0
+        # free_running: the ADC and the filter never stop (IMP/dsp_system_top.vhd:427-449) - a poll() that finds
+        # the frame gate closed still takes the next batch from the source, filters it (history carried)
+        # and drops its frames, as `sequencer` discards the FFT output between hand-shakes
+        # (IMP/sequencer_dsp.vhd:50-82).  Off: the source is only asked for samples that will be shown.
+        self.free_running = free_running
+        self.max_backlog = max_backlog    # frames kept for a slow consumer (GUI:687-689 trims its backlog the same way)
         self.stats = {"frames_received": 0, "frames_dropped": 0, "batches": 0, "samples": 0}
         print(f"GPU receiver opened: cuda:{device}, {channels} channel(s) x {fft_size} samples")
 
@@ -176,7 +183,12 @@ class GpuReceiver:
     def poll(self):
         """What UartReceiver.read_data + process_buffer do on the timer (GUI:616-689):
         returns the list of complete frames (bytes, 4 * fft_size each) now available."""
-        if not self.active or not self._armed():
+        if not self.active:
+            return []
+        if not self._armed():
+            if self.free_running and self.ctx.counters()["start"] > self._start_base:
+                self.process_batch()                               # the chain runs on; nobody takes the frames
+                self.stats["frames_dropped"] += self.channels
             return []
         out = self.process_batch()
         frames = out["frames"]
@@ -186,6 +198,17 @@ class GpuReceiver:
         got = [arr[c].tobytes() for c in range(self.channels)]
         self.stats["frames_received"] += len(got)
         return got
+
+    def poll_into_buffer(self):
+        """poll() for a consumer that drains `frame_buffer` at its own pace (the GUI's display loop): new
+        frames are appended; beyond `max_backlog` batches the oldest are dropped and counted, as
+        UartReceiver.process_buffer trims an overflowing buffer (GUI:687-689)."""
+        got = self.poll()
+        if got:
+            self.frame_buffer.append(got)
+            while len(self.frame_buffer) > self.max_backlog:
+                self.stats["frames_dropped"] += len(self.frame_buffer.pop(0))
+        return len(got)
 
 
 def frame_to_udp_payloads(frame: bytes):
