@@ -38,6 +38,7 @@ constexpr int kStreamMaxDeadband = 32;            // LSB; larger boundary differ
 // (32768 channels: 1.09 vs 1.03 ms, 49152: 1.63 vs 1.53 ms)
 constexpr int kLaneMinChannels = 28672;
 constexpr int kLaneMaxChannels = 57344;
+constexpr int kLaneBiasedMinChannels = 24576;     // k1_lane_biased from here up (measured crossover between 16384 and 32768)
 
 }  // namespace
 
@@ -392,6 +393,7 @@ int process_range(fra_ctx *ctx, const int16_t *d_in, int c0, int nch, int contin
         // k1_duo (stage pairs per warp) by default, k1_lane (a lane per channel) in the window of channel
         // counts where it wins; k1_stage and the stage-per-lane systolic k1_split only on request
         int variant = (nch >= kLaneMinChannels && nch < kLaneMaxChannels) ? 0 : 3;     // 0 lane, 1 split, 2 stage, 3 duo
+        // (the all-biased lane kernel wins from ~24k channels up, decided below once the coefficients are classified)
         if (ctx->flags & FRA_K1_FORCE_LANE) variant = 0;
         if (ctx->flags & FRA_K1_FORCE_SPLIT) variant = 1;
         if (ctx->flags & FRA_K1_FORCE_STAGE) variant = 2;
@@ -403,6 +405,10 @@ int process_range(fra_ctx *ctx, const int16_t *d_in, int c0, int nch, int contin
             // every operand biased, no FADD at all (fra_common.cuh: biquad_step_biased)
             biased = biased && biased_order_ok(sec.c[i][0], sec.c[i][1], sec.c[i][2], sec.c[i][3], sec.c[i][4]);
         }
+        // k1_lane_biased (whole-line staging, skewed cascade, every scheduler equally loaded) against k1_duo:
+        // 32768 channels 0.82 vs 0.97 ms, 65536 1.57 vs 1.70 ms; 16384 0.56 vs 0.49 ms (too few warps per scheduler)
+        if (biased && !(ctx->flags & (FRA_K1_FORCE_LANE | FRA_K1_FORCE_SPLIT | FRA_K1_FORCE_STAGE | FRA_K1_FORCE_DUO)))
+            variant = (nch >= kLaneBiasedMinChannels) ? 0 : 3;
         bool alt = true;                                           // ALPHA, BETA, ALPHA, BETA, ALPHA, BETA
         for (int i = 2; i < kStages; ++i) alt = alt && std::memcmp(sec.c[i], sec.c[i & 1], 5) == 0;
         if (variant == 3) {
@@ -1093,7 +1099,10 @@ int fra_iir_stream(fra_ctx *ctx, const int16_t *d_in, int16_t *d_out, size_t n, 
         return rc;
     }
 
-    const int chunk = 4096;
+    // Chunk length = samples per lane.  Long streams get short chunks so that there are lanes for the whole
+    // machine (2^26 samples / 512 = 131072 lanes); the scan cost per chunk (a few 24 x 24 products) is small
+    // against 512 samples of filtering.  Short streams keep 4096 (fewer boundaries, fewer LSB of dead band).
+    const int chunk = (n >= ((size_t)1 << 20)) ? 512 : 4096;
     const int n_chunks = (int)((n + chunk - 1) / chunk);
     const int n_warps = (n_chunks + 31) / 32;
     if (n_chunks > ctx->k1b_capacity) {
@@ -1106,7 +1115,7 @@ int fra_iir_stream(fra_ctx *ctx, const int16_t *d_in, int16_t *d_out, size_t n, 
         if (cudaMalloc((void **)&ctx->d_entry, (size_t)n_chunks * 24 * sizeof(int16_t)) != cudaSuccess ||
             cudaMalloc((void **)&ctx->d_exit, (size_t)n_chunks * 24 * sizeof(int16_t)) != cudaSuccess ||
             cudaMalloc((void **)&ctx->d_ends, (size_t)n_chunks * 24 * sizeof(float)) != cudaSuccess ||
-            cudaMalloc((void **)&ctx->d_aggr, (size_t)2 * n_warps * 24 * sizeof(float)) != cudaSuccess)
+            cudaMalloc((void **)&ctx->d_aggr, (size_t)4 * n_warps * 24 * sizeof(float)) != cudaSuccess)
             return FRA_ERR_NOMEM;
         ctx->k1b_capacity = n_chunks;
     }
@@ -1133,6 +1142,7 @@ int fra_iir_stream(fra_ctx *ctx, const int16_t *d_in, int16_t *d_out, size_t n, 
     a.continuous = continuous;
     a.apply_window = 1;
     a.iir = iir ? 1 : 0;
+    a.aggr_levels = 0;
     FRA_TRY(ctx, cudaMemsetAsync(ctx->d_counts, 0, 2 * sizeof(int), st));
 
     if (iir && n_chunks > 1) {
@@ -1173,13 +1183,27 @@ int fra_iir_stream(fra_ctx *ctx, const int16_t *d_in, int16_t *d_out, size_t n, 
             matmul(M, M, T);
             M = T;
         }
-        std::vector<float> mats((size_t)kScanMats * D * D);
+        std::vector<float> mats((size_t)kScanMats * D * D, 0.0f);
         M = R;                                                       // (A^L)^1
-        for (int lvl = 0; lvl < kScanMats; ++lvl) {
+        int aggr_levels = 0;
+        for (int lvl = 0; lvl < kScanMats; ++lvl) {                  // M^(1..16), then Q^(2^j) with Q = M^32
             for (int i = 0; i < D * D; ++i) mats[(size_t)lvl * D * D + i] = (float)M[i];
+            if (lvl >= kScanLevels) {
+                // a level of the aggregate scan matters while its matrix can move a state value (|s| <= 2^15,
+                // 24 terms) by more than a hundredth of an LSB, and while there are warps that far apart
+                double mx = 0.0;
+                for (int i = 0; i < D * D; ++i) mx = std::max(mx, std::fabs(M[i]));
+                if (mx * 24.0 * 32768.0 > 0.01 && (1 << (lvl - kScanLevels)) < n_warps) aggr_levels = lvl - kScanLevels + 1;
+            }
             matmul(M, M, T);
             M = T;
+            for (int i = 0; i < D * D; ++i)
+                if (!std::isfinite(M[i])) M[i] = 0.0;                // (cannot happen for r < 0.9995; keeps the table finite)
         }
+        if (aggr_levels == kAggrLevels && (1 << kAggrLevels) < n_warps) return FRA_ERR_UNSUPPORTED;   // stream too long for the table
+        // (two levels always run when there are warps to chain: with int8 coefficients and 512-sample chunks
+        // Q = A^16384 is negligible for every cascade this path accepts, and the scan code should not depend on that)
+        a.aggr_levels = std::max(aggr_levels, std::min(2, n_warps > 2 ? 2 : 0));
         FRA_TRY(ctx, cudaMemcpyAsync(ctx->d_mats, mats.data(), mats.size() * sizeof(float), cudaMemcpyHostToDevice, st));
         FRA_TRY(ctx, cudaStreamSynchronize(st));                    // `mats` lives on this stack frame
 
@@ -1189,9 +1213,22 @@ int fra_iir_stream(fra_ctx *ctx, const int16_t *d_in, int16_t *d_out, size_t n, 
         auto s0 = k1b_scan_warp<0>;
         FRA_LAUNCH(s0, dim3(n_warps), dim3(32), (size_t)0, st, a);
         FRA_TRY(ctx, cudaGetLastError());
-        auto sc = k1b_scan_carry;
-        FRA_LAUNCH(sc, dim3(1), dim3(32), (size_t)0, st, a);
-        FRA_TRY(ctx, cudaGetLastError());
+        {
+            // S_w = G_w + Q S_{w-1}: Hillis-Steele over the aggregates, ping-pong in aggr[2], aggr[3]
+            float *bufs[2] = {ctx->d_aggr + (size_t)2 * n_warps * 24, ctx->d_aggr + (size_t)3 * n_warps * 24};
+            const float *cur = ctx->d_aggr;                          // G_w
+            const dim3 g((unsigned)((n_warps + 3) / 4));
+            auto lv = k1b_aggr_level;
+            for (int j = 0; j < a.aggr_levels; ++j) {
+                FRA_LAUNCH(lv, g, dim3(128), (size_t)0, st, a, j, cur, bufs[j & 1]);
+                FRA_TRY(ctx, cudaGetLastError());
+                cur = bufs[j & 1];
+                ctx->last_kernels++;
+            }
+            auto cy = k1b_aggr_carry;
+            FRA_LAUNCH(cy, g, dim3(128), (size_t)0, st, a, cur);
+            FRA_TRY(ctx, cudaGetLastError());
+        }
         auto s1 = k1b_scan_warp<1>;
         FRA_LAUNCH(s1, dim3(n_warps), dim3(32), (size_t)0, st, a);
         FRA_TRY(ctx, cudaGetLastError());

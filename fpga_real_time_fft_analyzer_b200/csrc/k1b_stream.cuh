@@ -16,7 +16,8 @@
 //   1. k1b_lin_ends    one lane per chunk: e_p, by running the float model over the chunk
 //   2. k1b_scan_warp   inside each warp a Hillis-Steele scan by __shfl_up with the powers
 //                      (A^L)^1,2,4,8,16 (24x24, from the host, in shared memory);
-//      k1b_scan_carry  the warps' aggregates chained with (A^L)^32;
+//      k1b_aggr_level  the warps' aggregates chained with (A^L)^32 - again a Hillis-Steele scan,
+//                      one launch per level, stopped when the matrix power is negligible;
 //      k1b_scan_warp   again, with each warp's carry injected: the state at every chunk
 //                      boundary
 //   3. k1b_speculate   one lane per chunk: start from the rounded predicted state, filter
@@ -31,7 +32,8 @@ namespace fra {
 
 constexpr int kStateDim = 4 * kStages;      // (x1, x2, y1, y2) x 6 stages
 constexpr int kScanLevels = 5;              // lane distances 1, 2, 4, 8, 16
-constexpr int kScanMats = kScanLevels + 1;  // + (A^L)^32 for the carry across warps
+constexpr int kAggrLevels = 14;             // scan over the warps' aggregates: distances 1 .. 8192 warps (2^19 chunks)
+constexpr int kScanMats = kScanLevels + kAggrLevels;  // M^(1,2,4,8,16) with M = A^L, then Q^(1,2,4,...) with Q = M^32
 
 struct K1bArgs {
     const int16_t *in;      // [n]
@@ -43,8 +45,9 @@ struct K1bArgs {
     const int16_t *state0;  // [24] true state before sample 0 (used when continuous)
     int *stats;             // [0] chunks whose entry state differs from the neighbour's exit, [1] max |difference| (LSB)
     float *ends;            // [P][24] zero-state responses e_p, then predicted states s_p (in place)
-    float *aggr;            // [2][ceil(P/32)][24]: per-warp aggregates G_w, then carries C_w
-    const float *mats;      // [6][24][24] (A^L)^(1,2,4,8,16,32), row-major
+    float *aggr;            // [4][ceil(P/32)][24]: per-warp aggregates G_w, carries C_w, and the aggregate scan's two buffers
+    const float *mats;      // [kScanMats][24][24] row-major: M^(1,2,4,8,16), then Q^(2^j) with Q = M^32
+    int aggr_levels;        // levels of the aggregate scan that matter (Q^(2^j) not yet negligible), <= kAggrLevels
     unsigned long long n;   // samples
     int chunk;              // samples per chunk L (multiple of 8)
     int n_chunks;
@@ -115,6 +118,11 @@ FRA_DEV void stream_run(const K1bArgs &a, StageState (&st)[kStages], unsigned lo
         const uint4 xv = ldg128(a.in + n0);
         const unsigned xw[4] = {xv.x, xv.y, xv.z, xv.w};
         const int wbase = (int)(n0 & (unsigned long long)(kWindowLen - 1));
+        // the chunk's lanes sit at different window phases: eight ROM entries per lane and trip as two
+        // 16-byte loads (one scalar load per sample made the L1 the bottleneck of the small-chunk scan)
+        const int4 ra = __ldg(reinterpret_cast<const int4 *>(a.rom32 + wbase));
+        const int4 rb = __ldg(reinterpret_cast<const int4 *>(a.rom32 + wbase + 4));
+        const int rom8[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
         unsigned ow[4];
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
@@ -122,7 +130,7 @@ FRA_DEV void stream_run(const K1bArgs &a, StageState (&st)[kStages], unsigned lo
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 int x = e ? hi16(xw[h]) : lo16(xw[h]);
-                if (a.apply_window) x = window_int(x, __ldg(a.rom32 + wbase + 2 * h + e));
+                if (a.apply_window) x = window_int(x, rom8[2 * h + e]);
                 float v = small_int_to_float(x);
                 float acc = __int_as_float((x + 32768) + 0x4B400000);     // offset-binary, as biquad_step leaves it
                 if (a.iir) {
@@ -233,35 +241,40 @@ __global__ void __launch_bounds__(32) k1b_scan_warp(K1bArgs a)
     }
 }
 
-// the warps' aggregates chained, one warp, one state row per lane:
-//   S_w = G_w + M^32 S_{w-1}   (S_w = state at boundary 32 w + 31),   C_{w+1} = M S_w
-__global__ void __launch_bounds__(32) k1b_scan_carry(K1bArgs a)
+// The warps' aggregates chained:  S_w = G_w + Q S_{w-1}  (Q = M^32; S_w = state at boundary 32 w + 31).
+// Itself a scan - Hillis-Steele over the array of aggregates, one launch per level, one warp per
+// element (24 lanes = the 24 rows of the matrix-vector product), ping-pong between two buffers:
+//   level j:  X'[w] = X[w] + Q^(2^j) X[w - 2^j]   (w >= 2^j)
+// The host stops at the first level whose matrix is negligible (a.aggr_levels): for a stable
+// cascade and chunks of a few hundred samples Q = A^(32 L) is already zero to fp32 precision.
+__global__ void __launch_bounds__(128) k1b_aggr_level(K1bArgs a, int level, const float *src, float *dst)
 {
-    __shared__ float m1[kStateDim * kStateDim], m32[kStateDim * kStateDim], cur[kStateDim], nxt[kStateDim];
-    const int lane = threadIdx.x;
-    for (int i = lane; i < kStateDim * kStateDim; i += 32) {
-        m1[i] = __ldg(a.mats + i);
-        m32[i] = __ldg(a.mats + kScanLevels * kStateDim * kStateDim + i);
+    const int w = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (w + 1 >= a.n_warps || lane >= kStateDim) return;       // the last (possibly partial) warp hands nothing on
+    const int d = 1 << level;
+    float acc = src[(size_t)w * kStateDim + lane];
+    if (w >= d) {
+        const float *m = a.mats + (size_t)(kScanLevels + level) * kStateDim * kStateDim + lane * kStateDim;
+        const float *x = src + (size_t)(w - d) * kStateDim;
+#pragma unroll
+        for (int c = 0; c < kStateDim; ++c) acc = fmaf(__ldg(m + c), x[c], acc);
     }
-    if (lane < kStateDim) cur[lane] = 0.0f;
-    __syncwarp();
-    for (int w = 0; w + 1 < a.n_warps; ++w) {
-        if (lane < kStateDim) {
-            float acc = a.aggr[(size_t)w * kStateDim + lane];
-            if (w > 0)
-                for (int c = 0; c < kStateDim; ++c) acc = fmaf(m32[lane * kStateDim + c], cur[c], acc);
-            nxt[lane] = acc;
-        }
-        __syncwarp();
-        if (lane < kStateDim) cur[lane] = nxt[lane];
-        __syncwarp();
-        if (lane < kStateDim) {
-            float acc = 0.0f;
-            for (int c = 0; c < kStateDim; ++c) acc = fmaf(m1[lane * kStateDim + c], cur[c], acc);
-            a.aggr[(size_t)(a.n_warps + w + 1) * kStateDim + lane] = acc;
-        }
-        __syncwarp();
-    }
+    dst[(size_t)w * kStateDim + lane] = acc;
+}
+
+// carries  C_{w+1} = M S_w  (what lane 0 of warp w + 1 adds before its own scan)
+__global__ void __launch_bounds__(128) k1b_aggr_carry(K1bArgs a, const float *s_final)
+{
+    const int w = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (w + 1 >= a.n_warps || lane >= kStateDim) return;
+    const float *m = a.mats + lane * kStateDim;                // M^1
+    const float *x = s_final + (size_t)w * kStateDim;
+    float acc = 0.0f;
+#pragma unroll
+    for (int c = 0; c < kStateDim; ++c) acc = fmaf(__ldg(m + c), x[c], acc);
+    a.aggr[(size_t)(a.n_warps + w + 1) * kStateDim + lane] = acc;
 }
 
 // 3. exact filtering of chunk p from the scan's predicted state (chunk 0: the true state)

@@ -418,3 +418,21 @@ def test_fixed_point_fft_mode_bit_exact_vs_integer_oracle(n, rom):
         f.close()
     h = C.c_void_p()
     assert lib().fra_create(C.byref(h), 0, 1, 65536, _abi.FRA_FFT_FIXED16) == _abi.FRA_ERR_UNSUPPORTED
+
+
+def test_stream_scan_with_short_chunks_and_aggregate_levels(rom):
+    """2^20 samples: 512-sample chunks, 2048 lanes in 64 warps, the warps' aggregates chained by the
+    parallel scan.  Still inside the dead band of the truncating sections, chunk 0 exact."""
+    x = g.tone_noise([9], n=1 << 20, seed=4)[0]
+    yr, st = cg.window_iir(x[None], rom, 0x00, g.BANK0_COEFF, B1)
+    f = EmulFra(1, 16384)
+    try:
+        f.command(bytes([0x00]))
+        y, stats = f.iir_stream(x, exact=False)
+        assert stats["exact"] == 0 and stats["chunk"] == 512 and stats["n_chunks"] == 2048
+        assert 0 < stats["max_state_dev"] <= 32
+        assert np.abs(y.astype(int) - yr[0].astype(int)).max() <= 64
+        assert np.array_equal(y[:512], yr[0, :512])
+        assert np.abs(f.get_state()[0].astype(int) - st[0].astype(int)).max() <= 32
+    finally:
+        f.close()
