@@ -31,7 +31,6 @@ FRA_ROUND_NEAREST = 0x1
 FRA_K1_FORCE_LANE = 0x2
 FRA_K1_FORCE_SPLIT = 0x4
 FRA_K1_SPECULATE = 0x8
-FRA_K1_FORCE_STAGE = 0x10
 FRA_K1_FORCE_DUO = 0x20
 FRA_PIPELINE = 0x40
 FRA_K1_NO_BIASED = 0x80

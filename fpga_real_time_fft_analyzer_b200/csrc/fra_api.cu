@@ -84,6 +84,10 @@ struct fra_ctx {
     float *d_ends = nullptr, *d_aggr = nullptr, *d_mats = nullptr;
     int *d_counts = nullptr;
     int k1b_capacity = 0;
+    // the scan matrices on the device belong to these coefficients / this chunk length (recomputed only when they change)
+    int8_t k1b_key[36] = {0};
+    int k1b_key_chunk = 0;
+    double k1b_norm[32] = {0};        // max |entry| of each matrix of the table
 
     // FRA_PIPELINE: window+IIR of call i+1 beside the FFT of call i
     cudaStream_t pipe_k1 = nullptr, pipe_k2 = nullptr;
@@ -391,12 +395,11 @@ int process_range(fra_ctx *ctx, const int16_t *d_in, int c0, int nch, int contin
 #endif
         if (ctx->profiling) FRA_TRY(ctx, cudaEventRecord(ctx->ev[0], st));
         // k1_duo (stage pairs per warp) by default, k1_lane (a lane per channel) in the window of channel
-        // counts where it wins; k1_stage and the stage-per-lane systolic k1_split only on request
-        int variant = (nch >= kLaneMinChannels && nch < kLaneMaxChannels) ? 0 : 3;     // 0 lane, 1 split, 2 stage, 3 duo
+        // counts where it wins; the stage-per-lane systolic k1_split only on request (and for the exact single stream)
+        int variant = (nch >= kLaneMinChannels && nch < kLaneMaxChannels) ? 0 : 3;     // 0 lane, 1 split, 3 duo
         // (the all-biased lane kernel wins from ~24k channels up, decided below once the coefficients are classified)
         if (ctx->flags & FRA_K1_FORCE_LANE) variant = 0;
         if (ctx->flags & FRA_K1_FORCE_SPLIT) variant = 1;
-        if (ctx->flags & FRA_K1_FORCE_STAGE) variant = 2;
         if (ctx->flags & FRA_K1_FORCE_DUO) variant = 3;
         bool b1z = true, fast = true, biased = !(ctx->flags & FRA_K1_NO_BIASED);
         for (int i = 0; i < kStages; ++i) {
@@ -407,7 +410,7 @@ int process_range(fra_ctx *ctx, const int16_t *d_in, int c0, int nch, int contin
         }
         // k1_lane_biased (whole-line staging, skewed cascade, every scheduler equally loaded) against k1_duo:
         // 32768 channels 0.82 vs 0.97 ms, 65536 1.57 vs 1.70 ms; 16384 0.56 vs 0.49 ms (too few warps per scheduler)
-        if (biased && !(ctx->flags & (FRA_K1_FORCE_LANE | FRA_K1_FORCE_SPLIT | FRA_K1_FORCE_STAGE | FRA_K1_FORCE_DUO)))
+        if (biased && !(ctx->flags & (FRA_K1_FORCE_LANE | FRA_K1_FORCE_SPLIT | FRA_K1_FORCE_DUO)))
             variant = (nch >= kLaneBiasedMinChannels) ? 0 : 3;
         bool alt = true;                                           // ALPHA, BETA, ALPHA, BETA, ALPHA, BETA
         for (int i = 2; i < kStages; ++i) alt = alt && std::memcmp(sec.c[i], sec.c[i & 1], 5) == 0;
@@ -422,11 +425,6 @@ int process_range(fra_ctx *ctx, const int16_t *d_in, int c0, int nch, int contin
             static_assert(kDuoSmemRequest >= kDuoSmemBytes, "k1_duo shared memory");
             FRA_SMEM(ctx, kfn, kDuoSmemRequest);
             FRA_LAUNCH(kfn, dim3(grid), dim3(kDuoWarps * 32), (size_t)kDuoSmemRequest, st, k1);
-        } else if (variant == 2) {
-            const int grid = (nch + 31) / 32;
-            auto kfn = b1z ? k1_stage<true> : k1_stage<false>;
-            FRA_SMEM(ctx, kfn, kStageSmemBytes);
-            FRA_LAUNCH(kfn, dim3(grid), dim3(kStageWarps * 32), (size_t)kStageSmemBytes, st, k1);
         } else if (variant == 1) {
             const int per_cta = kSplitWarps * kSplitGroups;
             const int grid = (nch + per_cta - 1) / per_cta;
@@ -1147,65 +1145,74 @@ int fra_iir_stream(fra_ctx *ctx, const int16_t *d_in, int16_t *d_out, size_t n, 
 
     if (iir && n_chunks > 1) {
         // state-space matrices of the float model: one sample step A (24 x 24), then
-        // M = A^L and M^2 .. M^32 by squaring, in double
-        const CascadeCoef cc = a.coef;
-        auto step = [&](const double *in, double *out) {           // u = 0
-            double v = 0.0;
-            for (int sg = 0; sg < kStages; ++sg) {
-                const StageCoef &k = cc.set[sg];
-                const double x1 = in[4 * sg], x2 = in[4 * sg + 1], y1 = in[4 * sg + 2], y2 = in[4 * sg + 3];
-                const double y = (double)k.b2 * v + (double)k.b1 * x1 + (double)k.b0 * x2 + (double)k.na0 * y2 + (double)k.na1 * y1;
-                out[4 * sg] = v; out[4 * sg + 1] = x1; out[4 * sg + 2] = y; out[4 * sg + 3] = y1;
-                v = y;
-            }
-        };
+        // M = A^L and M^2 .. M^16, Q = M^32 and Q^2, Q^4, ... by squaring, in double.  Kept on the device
+        // until the coefficients or the chunk length change (a 2^26-sample call is 0.6 ms: the host-side
+        // powering and the upload would be a sixth of it).
         constexpr int D = kStateDim;
-        std::vector<double> A(D * D), M(D * D), T(D * D), R(D * D);
-        for (int j = 0; j < D; ++j) {
-            double e[D] = {0}, o[D];
-            e[j] = 1.0;
-            step(e, o);
-            for (int i = 0; i < D; ++i) A[i * D + j] = o[i];
-        }
-        auto matmul = [&](const std::vector<double> &x, const std::vector<double> &y, std::vector<double> &z) {
-            for (int i = 0; i < D; ++i)
-                for (int j = 0; j < D; ++j) {
-                    double acc = 0.0;
-                    for (int k = 0; k < D; ++k) acc += x[i * D + k] * y[k * D + j];
-                    z[i * D + j] = acc;
+        static_assert(kScanMats <= 32, "k1b_norm");
+        if (ctx->k1b_key_chunk != chunk || std::memcmp(ctx->k1b_key, sec.c, 36) != 0) {
+            const CascadeCoef cc = a.coef;
+            auto step = [&](const double *in, double *out) {           // u = 0
+                double v = 0.0;
+                for (int sg = 0; sg < kStages; ++sg) {
+                    const StageCoef &k = cc.set[sg];
+                    const double x1 = in[4 * sg], x2 = in[4 * sg + 1], y1 = in[4 * sg + 2], y2 = in[4 * sg + 3];
+                    const double y = (double)k.b2 * v + (double)k.b1 * x1 + (double)k.b0 * x2 + (double)k.na0 * y2 + (double)k.na1 * y1;
+                    out[4 * sg] = v; out[4 * sg + 1] = x1; out[4 * sg + 2] = y; out[4 * sg + 3] = y1;
+                    v = y;
                 }
-        };
-        // R = A^chunk by binary powering
-        for (int i = 0; i < D * D; ++i) R[i] = (i / D == i % D) ? 1.0 : 0.0;
-        M = A;
-        for (int e = chunk; e > 0; e >>= 1) {
-            if (e & 1) { matmul(R, M, T); R = T; }
-            matmul(M, M, T);
-            M = T;
-        }
-        std::vector<float> mats((size_t)kScanMats * D * D, 0.0f);
-        M = R;                                                       // (A^L)^1
-        int aggr_levels = 0;
-        for (int lvl = 0; lvl < kScanMats; ++lvl) {                  // M^(1..16), then Q^(2^j) with Q = M^32
-            for (int i = 0; i < D * D; ++i) mats[(size_t)lvl * D * D + i] = (float)M[i];
-            if (lvl >= kScanLevels) {
-                // a level of the aggregate scan matters while its matrix can move a state value (|s| <= 2^15,
-                // 24 terms) by more than a hundredth of an LSB, and while there are warps that far apart
-                double mx = 0.0;
-                for (int i = 0; i < D * D; ++i) mx = std::max(mx, std::fabs(M[i]));
-                if (mx * 24.0 * 32768.0 > 0.01 && (1 << (lvl - kScanLevels)) < n_warps) aggr_levels = lvl - kScanLevels + 1;
+            };
+            std::vector<double> A(D * D), M(D * D), T(D * D), R(D * D);
+            for (int j = 0; j < D; ++j) {
+                double e[D] = {0}, o[D];
+                e[j] = 1.0;
+                step(e, o);
+                for (int i = 0; i < D; ++i) A[i * D + j] = o[i];
             }
-            matmul(M, M, T);
-            M = T;
-            for (int i = 0; i < D * D; ++i)
-                if (!std::isfinite(M[i])) M[i] = 0.0;                // (cannot happen for r < 0.9995; keeps the table finite)
+            auto matmul = [&](const std::vector<double> &x, const std::vector<double> &y, std::vector<double> &z) {
+                for (int i = 0; i < D; ++i)
+                    for (int j = 0; j < D; ++j) {
+                        double acc = 0.0;
+                        for (int k = 0; k < D; ++k) acc += x[i * D + k] * y[k * D + j];
+                        z[i * D + j] = acc;
+                    }
+            };
+            // R = A^chunk by binary powering
+            for (int i = 0; i < D * D; ++i) R[i] = (i / D == i % D) ? 1.0 : 0.0;
+            M = A;
+            for (int e = chunk; e > 0; e >>= 1) {
+                if (e & 1) { matmul(R, M, T); R = T; }
+                matmul(M, M, T);
+                M = T;
+            }
+            std::vector<float> mats((size_t)kScanMats * D * D, 0.0f);
+            M = R;                                                       // (A^L)^1
+            for (int lvl = 0; lvl < kScanMats; ++lvl) {                  // M^(1..16), then Q^(2^j) with Q = M^32
+                double mx = 0.0;
+                for (int i = 0; i < D * D; ++i) {
+                    mats[(size_t)lvl * D * D + i] = (float)M[i];
+                    mx = std::max(mx, std::fabs(M[i]));
+                }
+                ctx->k1b_norm[lvl] = mx;
+                matmul(M, M, T);
+                M = T;
+                for (int i = 0; i < D * D; ++i)
+                    if (!std::isfinite(M[i])) M[i] = 0.0;                // (cannot happen for r < 0.9995; keeps the table finite)
+            }
+            FRA_TRY(ctx, cudaMemcpyAsync(ctx->d_mats, mats.data(), mats.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+            FRA_TRY(ctx, cudaStreamSynchronize(st));                    // `mats` lives on this stack frame
+            std::memcpy(ctx->k1b_key, sec.c, 36);
+            ctx->k1b_key_chunk = chunk;
         }
+        // a level of the aggregate scan matters while its matrix can move a state value (|s| <= 2^15, 24 terms)
+        // by more than a hundredth of an LSB, and while there are warps that far apart
+        int aggr_levels = 0;
+        for (int j = 0; j < kAggrLevels; ++j)
+            if (ctx->k1b_norm[kScanLevels + j] * 24.0 * 32768.0 > 0.01 && (1 << j) < n_warps) aggr_levels = j + 1;
         if (aggr_levels == kAggrLevels && (1 << kAggrLevels) < n_warps) return FRA_ERR_UNSUPPORTED;   // stream too long for the table
         // (two levels always run when there are warps to chain: with int8 coefficients and 512-sample chunks
         // Q = A^16384 is negligible for every cascade this path accepts, and the scan code should not depend on that)
         a.aggr_levels = std::max(aggr_levels, std::min(2, n_warps > 2 ? 2 : 0));
-        FRA_TRY(ctx, cudaMemcpyAsync(ctx->d_mats, mats.data(), mats.size() * sizeof(float), cudaMemcpyHostToDevice, st));
-        FRA_TRY(ctx, cudaStreamSynchronize(st));                    // `mats` lives on this stack frame
 
         auto l0 = k1b_lin_ends;
         FRA_LAUNCH(l0, dim3((n_chunks + 63) / 64), dim3(64), (size_t)0, st, a);

@@ -5,19 +5,20 @@
 // (IMP/filter_iir12.vhd:38-137, NEW/filter_iir12_cust.vhd:68-240) and the stream
 // mux of command_control (NEW/command_control.vhd:90-116).
 //
-// Three kernels, same arithmetic (fra_common.cuh):
-//   k1_stage  one warp per stage, one lane per channel, chunks handed from warp to warp
-//   k1_duo    k1_stage with two stages per warp (two independent chains per instruction stream)
-//             through shared memory: the kernel for channel counts that cannot fill
-//             the machine with k1_lane (the 4096-channel configuration).
-//   k1_lane   one warp lane per channel, all six stages in the lane's registers.
-//             ~50 issue slots per sample; needs >= ~19k channels to fill 148 SMs.
-//   k1_split  one warp lane per (channel, stage): a warp is five 6-lane systolic
-//             chains, stage s works on sample i-4s, outputs pass to the next lane
-//             by __shfl_up three iterations ahead of their use; input rows arrive by
-//             cp.async.bulk (TMA 1-D bulk copies on an mbarrier).  6x the parallelism for small channel counts (the
-//             4096-channel configuration), ~65 issue slots per sample.
-// Both read int16 [C][N] channel-major, write int16 [C][N], and carry the
+// Four kernels, same arithmetic (fra_common.cuh):
+//   k1_duo          a warp per PAIR of stages, one lane per channel, 64-sample chunks handed from warp to warp
+//                   through shared memory (loader, three stage pairs, writer): the kernel for channel counts
+//                   that cannot fill the machine with a lane per channel (up to ~24k channels).
+//   k1_lane_biased  one lane per channel, all six stages in the lane's registers as a SKEWED cascade (stage s on
+//                   sample i - s: six independent chains per warp), global memory in whole 128-byte lines through
+//                   a per-warp staging buffer, outputs in place: the kernel from ~24k channels up, for coefficient
+//                   sets that allow the all-biased step (the reference's fixed bank does).
+//   k1_lane         the general-step lane kernel (any int8 coefficients), sample-major, per-lane 32-byte fetches.
+//   k1_split        one lane per (channel, stage): a warp is five 6-lane systolic chains, stage s works on sample
+//                   i-4s, outputs pass to the next lane by __shfl_up three iterations ahead of their use; input rows
+//                   arrive by cp.async.bulk (TMA 1-D bulk copies on an mbarrier).  The EXACT single-stream path
+//                   (fra_iir_stream(exact = 1)) and on request.
+// All read int16 [C][N] channel-major, write int16 [C][N], and carry the
 // per-stage history (x[n-1], x[n-2], y[n-1], y[n-2]) in state[C][6][4].
 #pragma once
 #include "fra_common.cuh"
@@ -641,22 +642,11 @@ __global__ void __launch_bounds__(kSplitWarps * 32) k1_split(K1Args a)
     }
 }
 
-// ----------------------------------------------------------------- k1_stage
-// One WARP per stage, one lane per channel: a CTA is an eight-warp software pipeline over
-// 32 channels - warps 0 and 7 load + window half a chunk each, warps 1..6 run biquad stages
-// 1..6 (two warps per scheduler) - and chunks of
-// 64 samples move from warp to warp through double-buffered shared-memory tiles, one
-// __syncthreads() per chunk step.  Stage s works on chunk t-1-s at step t.  Compared with
-// k1_split there is no shuffle and no select in the recurrence loop (7.5 issue slots per
-// sample and warp instead of 11, all 32 lanes busy), and a scheduler that carries two of
-// the warps is issue-bound at about the same rate at which a lone warp is chain-bound.
+// ------------------------------------------------- shared-memory tiles of the pipelined kernel (k1_duo)
+// (k1_stage, round 1's one-warp-per-stage pipeline, was superseded by k1_duo at every channel count
+// and has been removed; its tile layout and chunk length live on here.)
 constexpr int kStageChunk = 64;                       // samples per pipeline step
-constexpr int kStageWarps = 2 + kStages;              // two loaders (half a chunk each) + six stages
 constexpr int kStageTileFloats = kStageChunk * 32;    // one chunk of 32 channels
-constexpr int kStageTilesBytes = kStages * 2 * kStageTileFloats * (int)sizeof(float);   // 6 boundaries x 2 buffers = 96 KiB
-constexpr int kStageRawBytes = 2 * 2 * (4 * 32 + 8) * 16;   // staging per loader and buffer: 4 x 32 lanes x 16 B of samples
-                                                            // + 8 x 16 B of window ROM (32 int32 entries)
-constexpr int kStageSmemBytes = kStageTilesBytes + kStageRawBytes;
 
 // tile layout: [sample / 4][channel][4] floats - lane c reads / writes 16 bytes at 16 c:
 // conflict-free 128-bit accesses, four consecutive samples of its channel per access
@@ -675,166 +665,10 @@ FRA_DEV void stage_convert8(uint4 x, int4 ra, int4 rb, float4 &fa, float4 &fb)
     fb.x = w(lo16(x.z), rb.x); fb.y = w(hi16(x.z), rb.y); fb.z = w(lo16(x.w), rb.z); fb.w = w(hi16(x.w), rb.w);
 }
 
-// half a chunk (32 samples = four 16-byte words per lane) into the loader->stage-0 tile
-template <bool QUIRK>
-FRA_DEV void stage_load_half(const uint4 (&pre)[4], const int4 *rom, float4 *tile)
-{
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int4 ra = rom[2 * q];            // shared memory, same address in every lane: broadcast
-        const int4 rb = rom[2 * q + 1];
-        float4 fa, fb;
-        stage_convert8<QUIRK>(pre[q], ra, rb, fa, fb);
-        tile[(2 * q) * 32] = fa;
-        tile[(2 * q + 1) * 32] = fb;
-    }
-}
-
-// One loader step: request chunk t+1 (cp.async into the other raw buffer), wait for chunk t's
-// copy, window + convert it into the loader->stage-0 tile.
-constexpr int kStageRawStride = 4 * 32 + 8;     // uint4 per staging buffer
-
-// One loader step: request chunk t+1 (cp.async of the samples AND of its 32 window ROM
-// entries into the other staging buffer), wait for chunk t's copies, window + convert it
-// into the loader->stage-0 tile.  Nothing the step needs comes through a register
-// scoreboard that a newer load could hold up.
-FRA_DEV void stage_loader_request(const int16_t *src, const int *rom32, int t, int half, uint4 *raw, int lane)
-{
-    const int i0 = t * kStageChunk + 32 * half;
-    uint4 *dstq = raw + (t & 1) * kStageRawStride;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) cp_async16(dstq + q * 32 + lane, src + (size_t)i0 + 8 * q);
-    if (lane < 8) cp_async16(dstq + 4 * 32 + lane, rom32 + ((i0 + 4 * lane) & (kWindowLen - 1)));
-}
-
-FRA_DEV void stage_loader_step(const int16_t *src, const int *rom32, int t, int n_chunks, int half, float *smem,
-                               uint4 *raw, int lane)
-{
-    if (t >= n_chunks) return;
-    if (t + 1 < n_chunks) stage_loader_request(src, rom32, t + 1, half, raw, lane);
-    cp_async_commit();
-    cp_async_wait<1>();                                        // everything but the group just committed: chunk t is here
-    __syncwarp();                                              // the ROM words were copied by lanes 0..7
-    const uint4 *srcq = raw + (t & 1) * kStageRawStride;
-    uint4 cur[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) cur[q] = srcq[q * 32 + lane];
-    const int4 *rom = reinterpret_cast<const int4 *>(srcq + 4 * 32);
-    float4 *tile = stage_tile(smem, 0, t & 1) + (8 * half) * 32 + lane;
-    const int w0 = (t * kStageChunk + 32 * half) & (kWindowLen - 1);
-    // ROM entries equal to -32768 live in [0, 15), [8178, 8206) and [16369, 16384)
-    const bool quirk = (w0 < 32) || (w0 >= 8160 && w0 < 8224) || (w0 >= kWindowLen - 32);
-    if (quirk) stage_load_half<true>(cur, rom, tile);
-    else stage_load_half<false>(cur, rom, tile);
-}
-
-// 16 samples of one stage: four float4 in, four float4 (or 32 packed bytes) out
-template <bool LAST, bool B1Z>
-FRA_DEV void stage_group16(const float4 (&in)[4], const StageCoef &k, StageState &st, float4 *tout, int16_t *gout,
-                           bool live)
-{
-    float acc[16], y[16];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        acc[4 * q + 0] = biquad_step<B1Z>(in[q].x, k, st, &y[4 * q + 0]);
-        acc[4 * q + 1] = biquad_step<B1Z>(in[q].y, k, st, &y[4 * q + 1]);
-        acc[4 * q + 2] = biquad_step<B1Z>(in[q].z, k, st, &y[4 * q + 2]);
-        acc[4 * q + 3] = biquad_step<B1Z>(in[q].w, k, st, &y[4 * q + 3]);
-    }
-    if (!LAST) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) tout[q * 32] = make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
-    } else if (live) {
-        uint4 o0, o1;
-        o0.x = pack16_acc(acc[0], acc[1]);   o0.y = pack16_acc(acc[2], acc[3]);
-        o0.z = pack16_acc(acc[4], acc[5]);   o0.w = pack16_acc(acc[6], acc[7]);
-        o1.x = pack16_acc(acc[8], acc[9]);   o1.y = pack16_acc(acc[10], acc[11]);
-        o1.z = pack16_acc(acc[12], acc[13]); o1.w = pack16_acc(acc[14], acc[15]);
-        stg128(gout, o0);
-        stg128(gout + 8, o1);
-    }
-}
-
-// one chunk (64 samples) of one stage, straight-line: inputs of group g+1 are in flight
-// while group g is filtered, and nothing is copied between iterations
-template <bool LAST, bool B1Z>
-FRA_DEV void stage_chunk(const float4 *tin, float4 *tout, int16_t *gout, const StageCoef &k, StageState &st, bool live)
-{
-    float4 buf[2][4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) buf[0][q] = tin[q * 32];
-#pragma unroll
-    for (int g = 0; g < kStageChunk / 16; ++g) {
-        if (g + 1 < kStageChunk / 16) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) buf[(g + 1) & 1][q] = tin[((g + 1) * 4 + q) * 32];
-        }
-        stage_group16<LAST, B1Z>(buf[g & 1], k, st, tout + (g * 4) * 32, gout + 16 * g, live);
-    }
-}
-
-template <bool B1Z>
-__global__ void __launch_bounds__(kStageWarps * 32, 2) k1_stage(K1Args a)
-{
-    FRA_DYN_SMEM(smem_raw);
-    float *smem = reinterpret_cast<float *>(smem_raw);
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const int c = blockIdx.x * 32 + lane;
-    const bool live = c < a.channels;
-    const int cc = live ? c : (a.channels - 1);                 // clamped: inactive lanes read valid memory
-    const int n_chunks = a.n / kStageChunk;
-    const int16_t *src = a.in + (size_t)cc * a.n;
-    int16_t *dst = a.out + (size_t)cc * a.n;
-
-    if (warp == 0 || warp == kStageWarps - 1) {
-        // ---- loaders: each owns half of every chunk; chunk t+1 is requested by cp.async
-        // (LDGSTS, no register scoreboard) before chunk t is converted, so the loads have a
-        // whole pipeline step to land.
-        const int half = (warp == 0) ? 0 : 1;
-        uint4 *raw = reinterpret_cast<uint4 *>(smem_raw + kStageTilesBytes) + half * (2 * kStageRawStride);
-        stage_loader_request(src, a.rom32, 0, half, raw, lane);                                  // chunk 0
-        cp_async_commit();
-        for (int t = 0; t < n_chunks + kStages; ++t) {
-            stage_loader_step(src, a.rom32, t, n_chunks, half, smem, raw, lane);
-            __syncthreads();
-        }
-    } else {
-        const int s = warp - 1;
-        const StageCoef k = a.coef.set[s];
-        StageState st = {0.0f, 0.0f, 0.0f, 0.0f};
-        if (a.continuous) {
-            const uint2 v = __ldg(reinterpret_cast<const uint2 *>(a.state + ((size_t)cc * kStages + s) * 4));
-            st.x1 = small_int_to_float(lo16(v.x));
-            st.x2 = small_int_to_float(hi16(v.x));
-            st.y1 = small_int_to_float(lo16(v.y));
-            st.y2 = small_int_to_float(hi16(v.y));
-        }
-        for (int t = 0; t < n_chunks + kStages; ++t) {
-            const int chunk = t - 1 - s;
-            if (chunk >= 0 && chunk < n_chunks) {
-                const float4 *tin = stage_tile(smem, s, chunk & 1) + lane;
-                if (s + 1 < kStages) {
-                    stage_chunk<false, B1Z>(tin, stage_tile(smem, s + 1, chunk & 1) + lane, nullptr, k, st, live);
-                } else {
-                    stage_chunk<true, B1Z>(tin, nullptr, dst + (size_t)chunk * kStageChunk, k, st, live);
-                }
-            }
-            __syncthreads();
-        }
-        if (live) {
-            uint2 v;
-            v.x = pack16((unsigned)(int)st.x1, (unsigned)(int)st.x2);
-            v.y = pack16((unsigned)(int)st.y1, (unsigned)(int)st.y2);
-            *reinterpret_cast<uint2 *>(a.state + ((size_t)c * kStages + s) * 4) = v;
-        }
-    }
-}
-
 // ------------------------------------------------------------------ k1_duo
-// k1_stage with TWO stages per warp, chained in registers.  A warp that runs one biquad
+// TWO stages per warp, chained in registers.  A warp that runs one biquad
 // recurrence is bound by the latency of its dependency chain (FFMA -> PRMT -> FADD, ~14-16
-// cycles per sample for 7.5 issue slots); k1_stage hides that by putting two stage warps on a
+// cycles per sample for 7.5 issue slots); round 1's k1_stage hid that by putting two single-stage warps on a
 // scheduler, and all eight warps then queue on the shared-memory pipe (12 tile accesses per
 // sample and CTA, l1tex ~2/3 busy).  Here a stage warp runs stages 2w and 2w+1 on the same
 // sample stream: stage 2w+1's recurrence trails stage 2w's by one sample, so the warp carries
@@ -900,7 +734,7 @@ FRA_DEV void duo_group16(const float4 (&in)[4], const StageCoef &ka, const Stage
     for (int q = 0; q < 4; ++q) tout[q * 32] = make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
 }
 
-// one chunk (64 samples) through a stage pair, straight-line like stage_chunk
+// one chunk (64 samples) through a stage pair, straight-line
 template <bool B1Z, int FAST>
 FRA_DEV void duo_chunk(const float4 *tin, float4 *tout, const StageCoef &ka, const StageCoef &kb, StageState &sa,
                        StageState &sb, float &ua, float &ub)

@@ -3,8 +3,8 @@
 // factors, scaled, truncation, pipelined streaming = radix-2^2, natural order, no overflow flag),
 // for users who want the FPGA's quantisation noise in the spectrum instead of an fp32 FFT
 // (SURVEY section 8 row f4).  PARITY UNPINNED vs xfft: the core is proprietary, its internal word
-// growth and truncation points are not published; the arithmetic here is defined by
-// oracle/fixed_fft.py (the -m gpu test is bit-exact against it) and documented in DESIGN.md:
+// growth and truncation points are not published; the arithmetic here is the one below, restated
+// as a numpy integer model for the tests (which are bit-exact against it) and documented in DESIGN.md:
 //   * decimation in frequency, pairs of radix-2 butterfly stages with the trivial -j rotation
 //     between them and one twiddle multiplier behind each pair;
 //   * int16 re / im between the pairs; inside a pair the two butterflies grow to 18 bits, the product

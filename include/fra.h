@@ -61,7 +61,7 @@ typedef enum fra_status {
 /* fra_create flags */
 #define FRA_ROUND_NEAREST   0x1u     /* int16 bins rounded to nearest-even instead of truncated (floor) */
 #define FRA_K1_FORCE_LANE   0x2u     /* always use the lane-per-channel window+IIR kernel */
-#define FRA_K1_FORCE_STAGE  0x10u    /* always use the warp-per-stage pipeline window+IIR kernel */
+/* 0x10u was FRA_K1_FORCE_STAGE (round 1's warp-per-stage kernel, superseded by the stage-pair kernel and removed) */
 #define FRA_K1_FORCE_DUO    0x20u    /* always use the two-stages-per-warp pipeline window+IIR kernel */
 #define FRA_PIPELINE        0x40u    /* fra_process runs the window+IIR of call i+1 beside the FFT of call i (which is
                                         enqueued by call i+1, or by fra_join / fra_sync after the last call) on two

@@ -54,7 +54,7 @@ def biased_edge_sections(rng):
 
 
 @pytest.mark.parametrize("flags,name", [(_abi.FRA_K1_FORCE_LANE, "lane"), (_abi.FRA_K1_FORCE_SPLIT, "split"),
-                                        (_abi.FRA_K1_FORCE_STAGE, "stage"), (_abi.FRA_K1_FORCE_DUO, "duo")])
+                                        (_abi.FRA_K1_FORCE_DUO, "duo")])
 @pytest.mark.parametrize("channels", [1, 6, 37])
 def test_k1_bit_exact_with_state_and_reload(flags, name, channels, rom):
     rng = np.random.default_rng(channels)
@@ -81,7 +81,7 @@ def test_k1_bit_exact_with_state_and_reload(flags, name, channels, rom):
         f.close()
 
 
-@pytest.mark.parametrize("flags", [_abi.FRA_K1_FORCE_LANE, _abi.FRA_K1_FORCE_SPLIT, _abi.FRA_K1_FORCE_STAGE,
+@pytest.mark.parametrize("flags", [_abi.FRA_K1_FORCE_LANE, _abi.FRA_K1_FORCE_SPLIT,
                                    _abi.FRA_K1_FORCE_DUO])
 def test_six_independent_sections(flags, rom):
     """fra_load_sections: every stage its own coefficients."""
@@ -198,7 +198,7 @@ def test_k1_random_coefficients_and_user_state(rom):
             coef[:] = [-128, 127, -128, -128, 60, 0, 127, -128, 127, 127, -60, 0]
         if trial == 4:
             coef[4], coef[10] = rng.integers(-60, 61, 2)
-        for flags in (_abi.FRA_K1_FORCE_LANE, _abi.FRA_K1_FORCE_SPLIT, _abi.FRA_K1_FORCE_STAGE, _abi.FRA_K1_FORCE_DUO,
+        for flags in (_abi.FRA_K1_FORCE_LANE, _abi.FRA_K1_FORCE_SPLIT, _abi.FRA_K1_FORCE_DUO,
                       _abi.FRA_K1_FORCE_SPLIT | _abi.FRA_K1_SPECULATE):      # speculation must roll back correctly
             f = EmulFra(c, n, flags)
             try:

@@ -43,11 +43,11 @@ def rel_l2(got, ref):
     return float(np.linalg.norm(got - ref) / np.linalg.norm(ref))
 
 
-@pytest.mark.parametrize("variant", ["lane", "split", "stage", "duo"])
+@pytest.mark.parametrize("variant", ["lane", "split", "duo"])
 @pytest.mark.parametrize("channels", [1, 5, 33, 257])
 def test_k1_bit_exact_state_reload(fra, rom, variant, channels):
     flags = {"lane": fra._abi.FRA_K1_FORCE_LANE, "split": fra._abi.FRA_K1_FORCE_SPLIT,
-             "stage": fra._abi.FRA_K1_FORCE_STAGE, "duo": fra._abi.FRA_K1_FORCE_DUO}[variant]
+             "duo": fra._abi.FRA_K1_FORCE_DUO}[variant]
     rng = np.random.default_rng(channels)
     n = 16384
     with fra.FraContext(channels, n, flags=flags) as ctx:
@@ -85,7 +85,7 @@ def test_k1_random_int8_coefficients_fuzz(fra, rom, seed):
         coef[:] = [127, -128, 127, 127, -60, 0, -128, 127, -128, -128, 60, 0]
     if seed >= 7:
         coef[4], coef[10] = rng.integers(-60, 61, 2)
-    for flags in (fra._abi.FRA_K1_FORCE_LANE, fra._abi.FRA_K1_FORCE_SPLIT, fra._abi.FRA_K1_FORCE_STAGE,
+    for flags in (fra._abi.FRA_K1_FORCE_LANE, fra._abi.FRA_K1_FORCE_SPLIT,
                   fra._abi.FRA_K1_FORCE_DUO,
                   fra._abi.FRA_K1_FORCE_SPLIT | fra._abi.FRA_K1_SPECULATE):
         with fra.FraContext(c, n, flags=flags) as ctx:
@@ -431,11 +431,11 @@ def test_process_host_async_matches_sync(fra, rom):
     assert np.array_equal(pending[0]["filtered"].numpy()[:8], y)
 
 
-@pytest.mark.parametrize("variant", ["lane", "split", "stage", "duo", "auto"])
+@pytest.mark.parametrize("variant", ["lane", "split", "duo", "auto"])
 def test_six_independent_sections(fra, rom, variant):
     """fra_load_sections: every stage its own coefficients, bit-exact."""
     flags = {"lane": fra._abi.FRA_K1_FORCE_LANE, "split": fra._abi.FRA_K1_FORCE_SPLIT,
-             "stage": fra._abi.FRA_K1_FORCE_STAGE, "duo": fra._abi.FRA_K1_FORCE_DUO, "auto": 0}[variant]
+             "duo": fra._abi.FRA_K1_FORCE_DUO, "auto": 0}[variant]
     rng = np.random.default_rng(31)
     c, n = 45, 16384
     with fra.FraContext(c, n, flags=flags) as ctx:

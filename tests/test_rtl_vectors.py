@@ -77,7 +77,7 @@ def test_bank0_constants_come_from_the_package(vec):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("variant", ["auto", "lane", "duo", "split", "stage"])
+@pytest.mark.parametrize("variant", ["auto", "lane", "duo", "split"])
 @pytest.mark.parametrize("key", CHAINS)
 def test_cuda_path_reproduces_the_vhdl_vectors(vec, key, variant):
     torch = pytest.importorskip("torch")
@@ -85,7 +85,7 @@ def test_cuda_path_reproduces_the_vhdl_vectors(vec, key, variant):
         pytest.fail("-m gpu tests need a CUDA device; there is no CPU fallback")
     from fpga_real_time_fft_analyzer_b200 import FraContext, _abi
     flags = {"auto": 0, "lane": _abi.FRA_K1_FORCE_LANE, "duo": _abi.FRA_K1_FORCE_DUO,
-             "split": _abi.FRA_K1_FORCE_SPLIT, "stage": _abi.FRA_K1_FORCE_STAGE}[variant]
+             "split": _abi.FRA_K1_FORCE_SPLIT}[variant]
     x, win, y, coef = vec[key + "_x"], vec[key + "_win"], vec[key + "_y"], vec[key + "_coef"]
     gap = bool(vec[key + "_gap"][0])
     c = 33                                               # the vector in channel 0, 17 and 32; noise elsewhere

@@ -22,7 +22,7 @@ ap.add_argument("--flags", type=lambda v: int(v, 0), default=0, help="extra fra_
 ap.add_argument("--hiccup", type=float, default=0.0, help="host sleep (s) every 40 steps inside the timed loop")
 a = ap.parse_args()
 flags = {"auto": 0, "lane": _abi.FRA_K1_FORCE_LANE, "split": _abi.FRA_K1_FORCE_SPLIT,
-         "spec": _abi.FRA_K1_SPECULATE | _abi.FRA_K1_FORCE_SPLIT, "stage": _abi.FRA_K1_FORCE_STAGE, "duo": _abi.FRA_K1_FORCE_DUO}[a.k1]
+         "spec": _abi.FRA_K1_SPECULATE | _abi.FRA_K1_FORCE_SPLIT, "duo": _abi.FRA_K1_FORCE_DUO}[a.k1]
 if a.pipeline:
     flags |= _abi.FRA_PIPELINE
 flags |= a.flags
