@@ -34,6 +34,8 @@ namespace fra {
 #ifndef FRA_K2_SEQ
 #define FRA_K2_SEQ 0
 #endif
+// (Capping the kernel at 112 registers - so that one of its CTAs fits beside three CTAs of the lane-per-channel
+// window+IIR kernel in pipelined mode - compiles without spills and changes nothing: 2.93 ms per step either way.)
 #ifndef FRA_K2_MINBLOCKS
 #define FRA_K2_MINBLOCKS 2
 #endif

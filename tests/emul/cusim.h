@@ -32,6 +32,7 @@
 #define __noinline__ __attribute__((noinline))
 #define __restrict__
 #define __launch_bounds__(...)
+#define __maxnreg__(...)
 #define __shared__ static
 #define __constant__ static
 #define __align__(n) __attribute__((aligned(n)))
