@@ -36,6 +36,7 @@ FRA_PIPELINE = 0x40
 FRA_K1_NO_BIASED = 0x80
 FRA_K2_STAGED = 0x100
 FRA_FFT_FIXED16 = 0x200
+FRA_K2_64K_SPLIT = 0x400
 
 
 class FraOutputs(C.Structure):

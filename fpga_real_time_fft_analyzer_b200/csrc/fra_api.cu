@@ -248,9 +248,43 @@ int launch_k2_n(fra_ctx *ctx, const K2Args &args, bool win, int qmode, cudaStrea
     return launch_k2_inst<LOG2N, false, 2>(ctx, args, st);
 }
 
-// N = 65536: split into even / odd 32K frames, the 32K kernel on both, radix-2 join
+#ifndef FRA_HOST_EMUL
+// N = 65536 on chip: one frame per cluster of two CTAs (k2_fft.cuh: k2_fft64k_cluster)
+template <bool WIN, int QMODE>
+int launch_k2_64k_cluster_inst(fra_ctx *ctx, K2Args args, cudaStream_t st)
+{
+    using P = FftPlan64kCluster;
+    const bool frames_only = args.frames && !args.iq && !args.mag && !args.phase;
+    auto kfn = frames_only ? k2_fft64k_cluster<WIN, QMODE, 0> : k2_fft64k_cluster<WIN, QMODE, 1>;
+    FRA_SMEM(ctx, kfn, P::SMEM_BYTES);
+    args.twn = ctx->d_twc;                                   // W_65536^e
+    if (args.batch <= 0) return FRA_OK;
+    kfn<<<dim3(2 * (unsigned)args.batch), dim3(P::THREADS), (size_t)P::SMEM_BYTES, st>>>(args);    // __cluster_dims__(2, 1, 1)
+    FRA_TRY(ctx, cudaGetLastError());
+    ctx->last_kernels++;
+    return FRA_OK;
+}
+
+int launch_k2_64k_cluster(fra_ctx *ctx, const K2Args &args, bool win, int qmode, cudaStream_t st)
+{
+    if (win) {
+        if (qmode == 0) return launch_k2_64k_cluster_inst<true, 0>(ctx, args, st);
+        if (qmode == 1) return launch_k2_64k_cluster_inst<true, 1>(ctx, args, st);
+        return launch_k2_64k_cluster_inst<true, 2>(ctx, args, st);
+    }
+    if (qmode == 0) return launch_k2_64k_cluster_inst<false, 0>(ctx, args, st);
+    if (qmode == 1) return launch_k2_64k_cluster_inst<false, 1>(ctx, args, st);
+    return launch_k2_64k_cluster_inst<false, 2>(ctx, args, st);
+}
+#endif
+
+// N = 65536 through HBM (FRA_K2_64K_SPLIT, and the host-emulated build): split into even / odd 32K frames,
+// the 32K kernel on both, radix-2 join
 int launch_k2_64k(fra_ctx *ctx, const K2Args &args, bool win, int qmode, cudaStream_t st)
 {
+#ifndef FRA_HOST_EMUL
+    if (!(ctx->flags & FRA_K2_64K_SPLIT)) return launch_k2_64k_cluster(ctx, args, win, qmode, st);
+#endif
     // scratch is indexed by the frame's position in the context, so channel slices on different
     // streams (fra_process_host) do not share it
     const size_t frames = (size_t)args.batch;
@@ -674,7 +708,12 @@ int fra_create(fra_ctx **out, int device, int n_channels, int fft_size, unsigned
         const size_t want_elems = frame_elems * ((flags & FRA_PIPELINE) ? 2 : 1);
         if (cudaMalloc((void **)&ctx->d_scratch, want_elems * sizeof(int16_t)) != cudaSuccess) return bail(FRA_ERR_NOMEM);
         ctx->scratch_elems = want_elems;
-        if (n > n_kernel) {
+#ifdef FRA_HOST_EMUL
+        const bool split64k = true;
+#else
+        const bool split64k = (flags & FRA_K2_64K_SPLIT) != 0;
+#endif
+        if (n > n_kernel && split64k) {
             if (cudaMalloc((void **)&ctx->d_split, (size_t)n_channels * 2 * kHalf64k * sizeof(int16_t)) != cudaSuccess ||
                 cudaMalloc((void **)&ctx->d_halves, (size_t)n_channels * 2 * kHalf64k * sizeof(float2)) != cudaSuccess)
                 return bail(FRA_ERR_NOMEM);

@@ -73,6 +73,26 @@ struct FftPlan {
     static constexpr int THREADS = ITEMS / 2;                  // two butterflies per thread per pass: 256 (512 at 32K)
     static constexpr int SMEM_BYTES = FPC * M * 8;
     static constexpr int SLOTS = FPC * (L / 2);                 // last-pass work items per CTA
+    static constexpr int FLOC = F;                              // sub-sequences held by one CTA (all of them)
+    static constexpr int MLOC = M;                              // complex points per frame in one CTA's buffer
+};
+
+// N = 65536 on chip: 32768 complex points are 256 KiB of fp32 - two CTAs of a thread-block cluster hold four
+// of the eight length-4096 sub-sequences each (128 KiB), run their sub-FFTs locally, and the last pass reads
+// the partner's half through distributed shared memory (k2_fft64k_cluster below).
+struct FftPlan64kCluster {
+    static constexpr int N = 65536;
+    static constexpr int M = N / 2;
+    static constexpr int L = 4096;
+    static constexpr int F = 8;
+    static constexpr int NB = L / 16;
+    static constexpr int PASSES = 3;
+    static constexpr int FPC = 1;
+    static constexpr int FLOC = 4;
+    static constexpr int MLOC = FLOC * L;
+    static constexpr int ITEMS = FLOC * NB;
+    static constexpr int THREADS = ITEMS / 2;                   // 512
+    static constexpr int SMEM_BYTES = MLOC * 8;                 // 128 KiB per CTA
 };
 
 // two packed int16 -> two floats: one I2F.S16 each, reading the register's low / high half
@@ -246,10 +266,9 @@ FRA_DEV float2 w16(int q)
 // constant.  Pass 0 reads the int16 frame from global memory, the others read shared memory; the
 // last pass of each size writes back to the positions it read, only the middle pass of L = 4096
 // scatters into other threads' read positions and needs a barrier between read and write.
-template <int LOG2N, bool WIN, int PASS>
-FRA_DEV void fft_pass(const K2Args &a, float2 *buf, int tid, int frame0, const uint2 *staged = nullptr)
+template <class P, bool WIN, int PASS>
+FRA_DEV void fft_pass(const K2Args &a, float2 *buf, int tid, int frame0, const uint2 *staged = nullptr, int f0 = 0)
 {
-    using P = FftPlan<LOG2N>;
     constexpr int IPT = P::ITEMS / P::THREADS;          // butterflies per thread per pass (2)
     // N = 16384: THREADS = NB and F = 2, so a thread's two butterflies are column j = tid of the
     // sub-sequences f = 0 and f = 1, whose input words are adjacent: one 64-bit load for both
@@ -276,21 +295,21 @@ FRA_DEV void fft_pass(const K2Args &a, float2 *buf, int tid, int frame0, const u
     auto compute = [&](int q, float2 (&o)[16], int &wbase, int &jlow) {
         const int it = tid + P::THREADS * q;
         const int j = it % P::NB;
-        const int f = (it / P::NB) % P::F;
-        const int fr = it / (P::NB * P::F);
-        const int base = fr * P::M + f * P::L;
+        const int f = (it / P::NB) % P::FLOC;               // sub-sequence within this CTA's buffer
+        const int fr = it / (P::NB * P::FLOC);
+        const int base = fr * P::MLOC + f * P::L;
         float2 v[16];
         if (PASS == 0) {
             const int frame = frame0 + fr;
             const bool live = frame < a.batch;
-            const uint32_t *src = a.in + (size_t)frame * P::M + (P::F * j + f);
+            const uint32_t *src = a.in + (size_t)frame * P::M + (P::F * j + f0 + f);
 #pragma unroll
             for (int r = 0; r < 16; ++r) {
                 unsigned w;
                 if constexpr (PAIRED) w = (q == 0) ? pre[r].x : pre[r].y;
                 else w = live ? __ldg(src + P::F * P::NB * r) : 0u;      // z[F (j + NB r) + f]
                 if (WIN) {
-                    const int e = P::F * (j + P::NB * r) + f;
+                    const int e = P::F * (j + P::NB * r) + f0 + f;
                     const int2 c = __ldg(reinterpret_cast<const int2 *>(a.rom32 + ((2 * e) & (kWindowLen - 1))));
                     v[r] = make_float2(small_int_to_float(window_int(lo16(w), c.x)),
                                        small_int_to_float(window_int(hi16(w), c.y)));
@@ -369,11 +388,12 @@ FRA_DEV void fft_pass(const K2Args &a, float2 *buf, int tid, int frame0, const u
 
 // OUT = 0: int16 frames only (the hot configuration); OUT = 1: any combination of
 // outputs, selected at run time by the null pointers in K2Args.
-// the last pass of the CTA's frames [frame0, frame0 + FPC): radix-F combine, untangle, mirror, pack
-template <int LOG2N, int QMODE, int OUT>
-FRA_DEV void fft_last_pass(const K2Args &a, const float2 *buf, int tid, int frame0)
+// the last pass of the CTA's frames [frame0, frame0 + FPC): radix-F combine, untangle, mirror, pack.
+// CLUSTER (FftPlan64kCluster): the eight sub-sequences live in two CTAs' buffers - f / 4 == rank in `buf`, the
+// others in `remote` (the partner's buffer through distributed shared memory) - and each CTA does half of the items.
+template <class P, int QMODE, int OUT, bool CLUSTER = false>
+FRA_DEV void fft_last_pass(const K2Args &a, const float2 *buf, int tid, int frame0, const float2 *remote = nullptr, int rank = 0)
 {
-    using P = FftPlan<LOG2N>;
 
     // ---------------- last pass: radix-F combine + untangle + mirror + pack
     BinOut out;
@@ -389,13 +409,18 @@ FRA_DEV void fft_last_pass(const K2Args &a, const float2 *buf, int tid, int fram
         const size_t up = (size_t)frame * P::N + k;
         const size_t dn = (size_t)frame * P::N - k;
         const int km = (P::L - k) & (P::L - 1);
-        const float2 *pk = buf + fr * P::M + swz(k);                   // f L is a multiple of 8 rows
-        const float2 *pm = buf + fr * P::M + swz(km);
+        const int sk = swz(k), skm = swz(km);                          // f L is a multiple of 8 rows
         float2 za[P::F], zb[P::F];
 #pragma unroll
         for (int f = 0; f < P::F; ++f) {
-            za[f] = pk[f * P::L];
-            zb[f] = pm[f * P::L];
+            if (CLUSTER) {
+                const float2 *b = ((f / P::FLOC) == rank) ? buf : remote;
+                za[f] = b[(f % P::FLOC) * P::L + sk];
+                zb[f] = b[(f % P::FLOC) * P::L + skm];
+            } else {
+                za[f] = buf[fr * P::M + f * P::L + sk];
+                zb[f] = buf[fr * P::M + f * P::L + skm];
+            }
             if (f > 0) {
                 // W_M^(f k) = W_N^(2 f k); f = 1 by squaring W_N^k, saving a load
                 const float2 w = (f == 1) ? make_float2(wn.x * wn.x - wn.y * wn.y, 2.0f * wn.x * wn.y)
@@ -448,21 +473,24 @@ FRA_DEV void fft_last_pass(const K2Args &a, const float2 *buf, int tid, int fram
     };
 
     // k = 1 .. L/2 - 1: uniform work; the twiddle of the next item is fetched one item ahead
+    // (in a cluster the two CTAs take alternate blocks of THREADS items)
     {
-        int slot = tid;
+        constexpr int SLOTS = P::FPC * (P::L / 2);
+        constexpr int STEP = CLUSTER ? 2 * P::THREADS : P::THREADS;
+        int slot = tid + (CLUSTER ? rank * P::THREADS : 0);
         float2 wn_next = __ldg(a.twn + (slot % (P::L / 2)));
 #pragma unroll 1
-        for (; slot < P::SLOTS; slot += P::THREADS) {
+        for (; slot < SLOTS; slot += STEP) {
             const int fr = slot / (P::L / 2);
             const int k = slot % (P::L / 2);
             const float2 wn = wn_next;
-            const int nslot = slot + P::THREADS;
-            if (nslot < P::SLOTS) wn_next = __ldg(a.twn + (nslot % (P::L / 2)));
+            const int nslot = slot + STEP;
+            if (nslot < SLOTS) wn_next = __ldg(a.twn + (nslot % (P::L / 2)));
             if (k != 0 && frame0 + fr < a.batch) item(fr, k, wn);
         }
     }
-    // the two self-paired items k = 0 and k = L/2 of every frame in the CTA
-    if (tid < 2 * P::FPC) {
+    // the two self-paired items k = 0 and k = L/2 of every frame in the CTA (in a cluster: one each)
+    if (tid < 2 * P::FPC && (!CLUSTER || (tid & 1) == rank)) {
         const int fr = tid >> 1;
         const int k = (tid & 1) ? (P::L / 2) : 0;
         if (frame0 + fr < a.batch) item(fr, k, __ldg(a.twn + k));
@@ -483,10 +511,10 @@ __global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS, (LOG2N == 15) ? 1 : F
     // ---------------------------------------------- radix-16 Stockham passes
     // (compile-time pass index: twiddle strides, swizzled offsets and the pass-specific store
     // pattern are all immediates; a run-time pass loop cost ~4 issue slots per sample)
-    fft_pass<LOG2N, WIN, 0>(a, buf, tid, frame0);
-    fft_pass<LOG2N, WIN, 1>(a, buf, tid, frame0);
-    if (P::PASSES == 3) fft_pass<LOG2N, WIN, 2>(a, buf, tid, frame0);
-    fft_last_pass<LOG2N, QMODE, OUT>(a, buf, tid, frame0);
+    fft_pass<P, WIN, 0>(a, buf, tid, frame0);
+    fft_pass<P, WIN, 1>(a, buf, tid, frame0);
+    if (P::PASSES == 3) fft_pass<P, WIN, 2>(a, buf, tid, frame0);
+    fft_last_pass<P, QMODE, OUT>(a, buf, tid, frame0);
 #ifdef FRA_TIMELINE
     timeline_mark(3, a.tl_step);
 #endif
@@ -527,22 +555,68 @@ __global__ void __launch_bounds__(FftPlan<kStagedLog2N>::THREADS, FRA_K2_MINBLOC
     for (; frame < a.batch; frame += (int)gridDim.x) {
         mbar_wait(bar, phase);                               // this frame's samples have landed
         phase ^= 1u;
-        fft_pass<kStagedLog2N, WIN, 0>(a, buf, tid, frame, raw);      // ends with a barrier: everyone has read `raw`
+        fft_pass<P, WIN, 0>(a, buf, tid, frame, raw);      // ends with a barrier: everyone has read `raw`
         const int next = frame + (int)gridDim.x;
         if (tid == 0 && next < a.batch) {
             fence_proxy_async();                             // the generic-proxy reads above before the bulk copy's writes
             mbar_expect_tx(bar, (unsigned)kStagedRawBytes);
             bulk_g2s(raw, a.in + (size_t)next * P::M, (unsigned)kStagedRawBytes, bar);
         }
-        fft_pass<kStagedLog2N, WIN, 1>(a, buf, tid, frame);
-        fft_pass<kStagedLog2N, WIN, 2>(a, buf, tid, frame);
-        fft_last_pass<kStagedLog2N, QMODE, OUT>(a, buf, tid, frame);
+        fft_pass<P, WIN, 1>(a, buf, tid, frame);
+        fft_pass<P, WIN, 2>(a, buf, tid, frame);
+        fft_last_pass<P, QMODE, OUT>(a, buf, tid, frame);
         __syncthreads();                                     // the last pass has read `buf` before the next frame's pass 0 writes it
     }
 #ifdef FRA_TIMELINE
     timeline_mark(3, a.tl_step);
 #endif
 }
+
+// ---------------------------------------------------- N = 65536 on chip (cluster of two CTAs)
+// One frame per 2-CTA thread-block cluster.  CTA `rank` owns the sub-sequences f = 4 rank .. 4 rank + 3 of
+// the eight (z[8 m + f], 4096 points each): three radix-16 passes in its own 128 KiB, exactly the code of the
+// single-CTA sizes.  After a cluster barrier the last pass - radix-8 combine, untangle, mirror, pack - takes
+// half of the items in each CTA and reads the partner's four sub-sequences through distributed shared memory
+// (64 KiB per CTA and frame over the SM-to-SM network); a second cluster barrier keeps both buffers alive
+// until both CTAs are done.  One HBM round trip per frame (2 B in, 4 B out per sample) instead of the 28 B of
+// the three-kernel path below.  a.twn = W_65536^e.
+#ifndef FRA_HOST_EMUL
+FRA_DEV unsigned cluster_ctarank()
+{
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+FRA_DEV void cluster_barrier()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// the partner CTA's copy of a shared-memory address of this CTA, as a generic pointer (DSMEM window)
+FRA_DEV const float2 *cluster_map(const float2 *p, unsigned rank)
+{
+    unsigned long long out;
+    asm volatile("mapa.u64 %0, %1, %2;" : "=l"(out) : "l"((unsigned long long)(uintptr_t)p), "r"(rank));
+    return reinterpret_cast<const float2 *>((uintptr_t)out);
+}
+
+template <bool WIN, int QMODE, int OUT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FftPlan64kCluster::THREADS, 1) k2_fft64k_cluster(K2Args a)
+{
+    using P = FftPlan64kCluster;
+    FRA_DYN_SMEM(smem_raw);
+    float2 *buf = reinterpret_cast<float2 *>(smem_raw);
+    const int tid = threadIdx.x;
+    const int rank = (int)cluster_ctarank();
+    const int frame = blockIdx.x >> 1;                       // both CTAs of a cluster: the same frame, never past the batch
+    fft_pass<P, WIN, 0>(a, buf, tid, frame, nullptr, P::FLOC * rank);
+    fft_pass<P, WIN, 1>(a, buf, tid, frame, nullptr, P::FLOC * rank);
+    fft_pass<P, WIN, 2>(a, buf, tid, frame, nullptr, P::FLOC * rank);
+    cluster_barrier();                                       // both halves of the frame are transformed
+    const float2 *remote = cluster_map(buf, (unsigned)(rank ^ 1));
+    fft_last_pass<P, QMODE, OUT, true>(a, buf, tid, frame, remote, rank);
+    cluster_barrier();                                       // nobody leaves while the partner still reads its buffer
+}
+#endif
 
 // ------------------------------------------------------------------ N = 65536
 // A 64K frame is 32768 complex points = 256 KiB of fp32, more than an SM's shared memory, so it
