@@ -77,8 +77,8 @@ def main():
     print(f"\nexecuted warp instructions by opcode (total {tot}):")
     for op, n in ops.most_common(24):
         print(f"  {op:10s} {n:12d}  {100.0 * n / tot:5.1f} %")
-    evidence = [op for op in ops if op in ("UBLKCP", "UTMALDG", "UTMASTG", "SYNCS", "UTCHMMA", "LDTM", "HMMA")]
-    print("\nBlackwell-specific opcodes present:", ", ".join(sorted(evidence)) or "none")
+    evidence = [op for op in ops if op in ("UBLKCP", "UTMALDG", "UTMASTG", "SYNCS", "UTCHMMA", "LDTM", "HMMA", "FADD2", "FFMA2", "FMUL2", "LDGSTS")]
+    print("\nBlackwell-specific / async-copy opcodes present (FADD2 = packed fp32x2, UBLKCP = cp.async.bulk, LDGSTS = cp.async):", ", ".join(sorted(evidence)) or "none")
 
 
 if __name__ == "__main__":
