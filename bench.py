@@ -327,7 +327,13 @@ def run_ours(args):
     # ---- per-kernel durations: events recorded inside the library around each kernel on a sequential
     # context of the same size (each kernel alone on the GPU; in the pipelined loop the two overlap
     # and a kernel's own span is not its cost)
-    seq = FraContext(channels, N, device=local)
+    # The e2e context sends the frames as bins 0..N/2 + one bit per bin and completes the Hermitian half on the
+    # host (FRA_HOST_HALF_SPECTRUM: byte-identical frames, 2.06 instead of 4 B per sample device-to-host) when at
+    # most two ranks share the host: the mirror costs host cores and memory bandwidth, which eight ranks on
+    # one host do not have to spare (there the link is not the bottleneck, the host is).  FRA_BENCH_HALF=0/1 overrides.
+    half_env = os.environ.get("FRA_BENCH_HALF")
+    use_half = (world <= 2) if half_env is None else (half_env == "1")
+    seq = FraContext(channels, N, device=local, flags=_abi.FRA_HOST_HALF_SPECTRUM if use_half else 0)
     seq.command(0x00)
     seq.profile(True)
     k1_ms, k2_ms = [], []
@@ -365,7 +371,8 @@ def run_ours(args):
     e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0) / e2e_steps)
     e2e_value = TOTAL_CHANNELS * N / (e2e_ms * 1e-3) / 1e9
     # aggregate host-link traffic of all ranks during the e2e loop (every rank shares one host)
-    host_gbs = sum_over_ranks(channels * N * 6 / (e2e_ms * 1e-3) / 1e9)
+    d2h_per_frame = ((N // 2 + 1) * 4 + N // 16) if use_half else 4 * N
+    host_gbs = sum_over_ranks(channels * (N * 2 + d2h_per_frame) / (e2e_ms * 1e-3) / 1e9)
     seq.close()
     del x_host, pending, cur
     seq._pinned = {}
@@ -425,8 +432,11 @@ def run_ours(args):
                                  "sample": f"numpy/scipy float64 chain (history carried), {cores} processes x {CPU_REPS} x 64 channels x {N} samples ({cpu_dt:.1f} s wall, {cpu_dt * cores:.0f} core-seconds)",
                                  "int_golden_1core": cpu_int_rate()},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": channels * N * 2,
-                        "d2h_bytes_per_step": channels * N * 4, "steps": e2e_steps,
-                        "host_link_gbs_all_ranks": host_gbs},
+                        "d2h_bytes_per_step": channels * d2h_per_frame, "steps": e2e_steps,
+                        "host_link_gbs_all_ranks": host_gbs,
+                        "frames": ("bins 0..N/2 + 1 bit per bin over PCIe, Hermitian half completed by the host inside host_wait "
+                                   "(FRA_HOST_HALF_SPECTRUM); the caller gets the full 65536-byte frames" if use_half
+                                   else "full 65536-byte frames over PCIe")},
                 "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms, "warmup_steps_run": warmup_run, "clocks": clocks}
         emit(line)
     if world > 1:

@@ -37,6 +37,7 @@ FRA_K1_NO_BIASED = 0x80
 FRA_K2_STAGED = 0x100
 FRA_FFT_FIXED16 = 0x200
 FRA_K2_64K_SPLIT = 0x400
+FRA_HOST_HALF_SPECTRUM = 0x800
 
 
 class FraOutputs(C.Structure):

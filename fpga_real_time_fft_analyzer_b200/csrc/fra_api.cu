@@ -17,8 +17,13 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <thread>
 #include <utility>
 #include <vector>
+#if !defined(FRA_HOST_EMUL) && (defined(__x86_64__) || defined(_M_X64))
+#include <immintrin.h>
+#define FRA_HAVE_AVX2_PATH 1
+#endif
 
 namespace {
 
@@ -102,6 +107,11 @@ struct fra_ctx {
     cudaEvent_t host_done[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
     unsigned long long host_calls = 0;
     size_t scratch_elems = 0;         // int16 elements allocated at d_scratch
+    // FRA_HOST_HALF_SPECTRUM: mirror bits on the device, their pinned host copies per call slot, and the frames
+    // (host pointer) of each slot that still wait for their upper half
+    uint32_t *d_mbits = nullptr;
+    uint32_t *h_mbits[2] = {nullptr, nullptr};
+    uint8_t *mirror_frames[2] = {nullptr, nullptr};
 
     bool profiling = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // K1 begin/end, K2 begin/end
@@ -564,12 +574,84 @@ cudaError_t pipe_host_join(fra_ctx *ctx)
 }
 
 // host waits for the copy streams (calls of fra_process_host_async still in flight)
+void host_mirror(fra_ctx *ctx, int slot);
+
 cudaError_t host_streams_join(fra_ctx *ctx)
 {
     cudaError_t e = cudaSuccess;
     for (auto st : ctx->copy_streams)
         if (st && e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess)
+        for (int slot = 0; slot < 2; ++slot) host_mirror(ctx, slot);   // frames of half-spectrum calls nobody waited for
     return e;
+}
+
+// ---- FRA_HOST_HALF_SPECTRUM, host side: the upper half of every frame from bins 0 .. N/2 and the mirror bits.
+// word j = {re, im} (int16 pair);  X[N-j] = {re, -im - bit_j} mod 2^16  ((~im) + 1 - bit in the upper half-word).
+inline uint32_t mirror_word(uint32_t w, uint32_t bit) { return (w & 0xFFFFu) | ((((~w) >> 16) + 1u - bit) << 16); }
+
+void mirror_frame_scalar(uint32_t *fr, const uint32_t *bits, int n, int j0, int j1)
+{
+    for (int j = j0; j < j1; ++j) fr[n - j] = mirror_word(fr[j], (bits[j >> 5] >> (j & 31)) & 1u);
+}
+
+#ifdef FRA_HAVE_AVX2_PATH
+__attribute__((target("avx2"))) void mirror_frame_avx2(uint32_t *fr, const uint32_t *bits, int n)
+{
+    const int m = n / 2;
+    mirror_frame_scalar(fr, bits, n, 1, 8);
+    const __m256i lo = _mm256_set1_epi32(0xFFFF), one = _mm256_set1_epi32(1);
+    const __m256i sh = _mm256_setr_epi32(0, 1, 2, 3, 4, 5, 6, 7), rev = _mm256_setr_epi32(7, 6, 5, 4, 3, 2, 1, 0);
+    for (int j = 8; j < m; j += 8) {                                   // words j .. j+7 -> N-j-7 .. N-j
+        const __m256i w = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(fr + j));
+        const __m256i b = _mm256_and_si256(_mm256_srlv_epi32(_mm256_set1_epi32((int)((bits[j >> 5] >> (j & 31)) & 0xFFu)), sh), one);
+        const __m256i hi = _mm256_add_epi32(_mm256_srli_epi32(_mm256_xor_si256(w, _mm256_set1_epi32(-1)), 16), _mm256_sub_epi32(one, b));
+        const __m256i r = _mm256_or_si256(_mm256_and_si256(w, lo), _mm256_slli_epi32(hi, 16));
+        _mm256_storeu_si256(reinterpret_cast<__m256i *>(fr + n - j - 7), _mm256_permutevar8x32_epi32(r, rev));
+    }
+}
+#endif
+
+// all frames of one call slot, the frames split over the host's threads
+void host_mirror(fra_ctx *ctx, int slot)
+{
+    uint8_t *base = ctx->mirror_frames[slot];
+    if (!base) return;
+    ctx->mirror_frames[slot] = nullptr;
+    const int n = ctx->n, words = n / 64;                              // N/2 bits per frame
+    const size_t C = (size_t)ctx->channels;
+    const uint32_t *bits = ctx->h_mbits[slot];
+#ifdef FRA_HAVE_AVX2_PATH
+    const bool avx2 = __builtin_cpu_supports("avx2");
+#endif
+    auto work = [&](size_t f0, size_t f1) {
+        for (size_t f = f0; f < f1; ++f) {
+            uint32_t *fr = reinterpret_cast<uint32_t *>(base + f * (size_t)n * 4);
+#ifdef FRA_HAVE_AVX2_PATH
+            if (avx2) { mirror_frame_avx2(fr, bits + f * words, n); continue; }
+#endif
+            mirror_frame_scalar(fr, bits + f * words, n, 1, n / 2);
+        }
+    };
+    const size_t hw = std::max(1u, std::thread::hardware_concurrency());
+    const size_t n_thr = std::min<size_t>(std::min<size_t>(hw, 32), std::max<size_t>(1, C * (size_t)n >> 20));
+    if (n_thr <= 1) { work(0, C); return; }
+    std::vector<std::thread> pool;
+    const size_t per = (C + n_thr - 1) / n_thr;
+    for (size_t t = 0; t < n_thr; ++t) {
+        const size_t f0 = t * per, f1 = std::min(C, f0 + per);
+        if (f0 < f1) pool.emplace_back(work, f0, f1);
+    }
+    for (auto &th : pool) th.join();
+}
+
+// everything an earlier call left in slot `slot`: its copies have landed, its frames are whole
+int finish_host_slot(fra_ctx *ctx, int slot)
+{
+    for (cudaEvent_t e : ctx->host_done[slot])
+        if (e) FRA_TRY(ctx, cudaEventSynchronize(e));
+    host_mirror(ctx, slot);
+    return FRA_OK;
 }
 
 fra_outputs offset_outputs(const fra_outputs &o, size_t c0, int n)
@@ -737,7 +819,9 @@ int fra_destroy(fra_ctx *ctx)
         if (ps) { cudaStreamSynchronize(ps); cudaStreamDestroy(ps); }
     for (cudaEvent_t pe : {ctx->pipe_in, ctx->pipe_go, ctx->pipe_k1_done[0], ctx->pipe_k1_done[1], ctx->pipe_k2_done[0], ctx->pipe_k2_done[1]})
         if (pe) cudaEventDestroy(pe);
-    void *bufs[] = {ctx->d_rom32, ctx->d_rom2x, ctx->d_twfx, ctx->d_state, ctx->d_scratch, ctx->d_tw1, ctx->d_tw2, ctx->d_twn, ctx->d_in, ctx->d_twc, ctx->d_halves, ctx->d_split,
+    for (auto hb : ctx->h_mbits)
+        if (hb) cudaFreeHost(hb);
+    void *bufs[] = {ctx->d_rom32, ctx->d_rom2x, ctx->d_twfx, ctx->d_mbits, ctx->d_state, ctx->d_scratch, ctx->d_tw1, ctx->d_tw2, ctx->d_twn, ctx->d_in, ctx->d_twc, ctx->d_halves, ctx->d_split,
                     ctx->d_frames, ctx->d_filtered_out, ctx->d_iq, ctx->d_mag, ctx->d_phase, ctx->d_entry,
                     ctx->d_exit, ctx->d_counts, ctx->d_ends, ctx->d_aggr, ctx->d_mats};
     for (void *p : bufs)
@@ -971,9 +1055,7 @@ int fra_host_wait(fra_ctx *ctx, uint64_t ticket)
     if (!ctx || ticket == 0 || ticket > ctx->host_calls) return FRA_ERR_INVALID;
     if (ticket + 2 <= ctx->host_calls) return FRA_OK;          // its slot was waited for when it was reused
     FRA_TRY(ctx, cudaSetDevice(ctx->device));
-    for (cudaEvent_t e : ctx->host_done[ticket & 1])
-        if (e) FRA_TRY(ctx, cudaEventSynchronize(e));
-    return FRA_OK;
+    return finish_host_slot(ctx, (int)(ticket & 1));
 }
 
 int fra_process_host_async(fra_ctx *ctx, const int16_t *h_in, int continuous, int log2_scale,
@@ -997,6 +1079,22 @@ int fra_process_host_async(fra_ctx *ctx, const int16_t *h_in, int continuous, in
     if (iir && !h_out->d_filtered && !ctx->d_scratch) {
         if (cudaMalloc((void **)&ctx->d_scratch, C * n * 2) != cudaSuccess) return FRA_ERR_NOMEM;
         ctx->scratch_elems = C * n;
+    }
+    // the slot this call takes was last used two calls ago: that call is finished first (its events, its mirror)
+    const unsigned long long id = ctx->host_calls + 1;
+    {
+        int rc0 = finish_host_slot(ctx, (int)(id & 1));
+        if (rc0 != FRA_OK) return rc0;
+    }
+    // half-spectrum transfer of the frames: only with the truncating 1/N-or-smaller scale, where the mirrored
+    // imaginary part is -im or -im - 1 (a saturating or rounding quantiser breaks that relation)
+    const bool half = (ctx->flags & FRA_HOST_HALF_SPECTRUM) && h_out->d_frames && !(ctx->flags & (FRA_ROUND_NEAREST | FRA_FFT_FIXED16)) &&
+                      log2_scale <= -ctx->log2n;
+    const size_t mwords = n / 64;                                     // mirror bits per frame, in words
+    if (half) {
+        if (!need((void **)&ctx->d_mbits, C * mwords * 4)) return FRA_ERR_NOMEM;
+        for (auto &hb : ctx->h_mbits)
+            if (!hb && cudaMallocHost((void **)&hb, C * mwords * 4) != cudaSuccess) return FRA_ERR_NOMEM;
     }
 
     fra_outputs dev;
@@ -1026,7 +1124,21 @@ int fra_process_host_async(fra_ctx *ctx, const int16_t *h_in, int continuous, in
         if (rc != FRA_OK) break;
         if (h_out->d_filtered)
             FRA_TRY(ctx, cudaMemcpyAsync(h_out->d_filtered + c0 * n, o.d_filtered, nch * n * 2, cudaMemcpyDeviceToHost, st));
-        if (h_out->d_frames)
+        if (h_out->d_frames && half) {
+            // bins 0 .. N/2 of every frame straight into the caller's frames (a pitched copy), the mirror bits
+            // into the slot's staging; fra_host_wait completes the upper halves on the host's cores
+            const size_t total = nch * (n / 2);
+            auto kfn = k3_mirror_bits;
+            int log2m = ctx->log2n - 1;
+            FRA_LAUNCH(kfn, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)0, st,
+                       (const uint32_t *)o.d_frames, ctx->d_mbits + c0 * mwords, total, log2m);
+            FRA_TRY(ctx, cudaGetLastError());
+            ctx->last_kernels++;
+            FRA_TRY(ctx, cudaMemcpy2DAsync(h_out->d_frames + c0 * n * 4, n * 4, o.d_frames, n * 4, (n / 2 + 1) * 4, nch,
+                                           cudaMemcpyDeviceToHost, st));
+            FRA_TRY(ctx, cudaMemcpyAsync(ctx->h_mbits[id & 1] + c0 * mwords, ctx->d_mbits + c0 * mwords, nch * mwords * 4,
+                                         cudaMemcpyDeviceToHost, st));
+        } else if (h_out->d_frames)
             FRA_TRY(ctx, cudaMemcpyAsync(h_out->d_frames + c0 * n * 4, o.d_frames, nch * n * 4, cudaMemcpyDeviceToHost, st));
         if (h_out->d_iq)
             FRA_TRY(ctx, cudaMemcpyAsync(h_out->d_iq + c0 * n * 2, o.d_iq, nch * n * 8, cudaMemcpyDeviceToHost, st));
@@ -1040,13 +1152,12 @@ int fra_process_host_async(fra_ctx *ctx, const int16_t *h_in, int continuous, in
         return rc;
     }
     // completion of THIS call on every copy stream; at most two calls are in flight
-    const unsigned long long id = ctx->host_calls + 1;
     for (int s = 0; s < 3; ++s) {
         cudaEvent_t &e = ctx->host_done[id & 1][s];
         if (!e) FRA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        else FRA_TRY(ctx, cudaEventSynchronize(e));           // the call two before this one
         FRA_TRY(ctx, cudaEventRecord(e, ctx->copy_streams[s]));
     }
+    if (half) ctx->mirror_frames[id & 1] = h_out->d_frames;
     ctx->host_calls = id;
     *ticket = id;
     return FRA_OK;

@@ -666,4 +666,26 @@ __global__ void __launch_bounds__(256) k2_join64k(const float2 *halves, const fl
     emit_pair<QMODE>(out, base, 0, kHalf64k, 0, false, make_float2(2.0f * (e.x - o.x), 2.0f * (e.y - o.y)));
 }
 
+// ------------------------------------------------- half-spectrum host transfer (FRA_HOST_HALF_SPECTRUM)
+// The input is real, so X[N-j] = conj(X[j]) - up to the truncation: the frame holds floor(Im s) at j and
+// floor(-Im s) at N - j, which is -floor(Im s) - 1 unless Im s is an integer.  One bit per bin says which:
+// bit j = (im[j] + im[N-j] != 0 mod 2^16), taken from the finished frame itself, so the host can rebuild the
+// upper half exactly from bins 0..N/2 and N/2 bits per frame - 33 KiB over PCIe instead of 64 KiB.
+// One thread per lower-half bin, one word per warp (ballot).
+__global__ void __launch_bounds__(256) k3_mirror_bits(const uint32_t *frames, uint32_t *bits, size_t total, int log2m)
+{
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // total is a multiple of 32
+    if (t >= total) return;
+    const size_t frame = t >> log2m;
+    const unsigned j = (unsigned)(t & (((size_t)1 << log2m) - 1));
+    const uint32_t *fr = frames + (frame << (log2m + 1));
+    unsigned nz = 0;
+    if (j != 0) {
+        const unsigned a = fr[j] >> 16, b = fr[((size_t)2 << log2m) - j] >> 16;
+        nz = ((a + b) & 0xFFFFu) != 0;
+    }
+    const unsigned word = __ballot_sync(0xffffffffu, nz);
+    if ((threadIdx.x & 31) == 0) bits[t >> 5] = word;
+}
+
 }  // namespace fra

@@ -79,6 +79,12 @@ typedef enum fra_status {
 #define FRA_K2_STAGED       0x100u   /* 16K frames: persistent FFT CTAs whose frames arrive by one bulk copy each (cp.async.bulk on an
                                         mbarrier) instead of one frame per CTA with per-thread loads; same results, measured
                                         slower on B200, kept for A/B timing */
+#define FRA_HOST_HALF_SPECTRUM 0x800u /* fra_process_host[_async]: the int16 frames cross PCIe as bins 0..N/2 plus one bit per bin
+                                        (33 KiB instead of 64 KiB per 16K frame) and fra_host_wait completes the Hermitian upper
+                                        half on the host's cores - X[N-j] = {re, -im - bit}, the bit saying whether floor(-Im s)
+                                        is -floor(Im s) or one less.  Byte-identical frames; only with the default truncating
+                                        scale (otherwise, and for the other outputs, the full transfer is used).  Pays when the
+                                        device-to-host link is the bottleneck and the host has cores and memory bandwidth to spare. */
 #define FRA_K2_64K_SPLIT     0x400u   /* 64K frames through HBM (even / odd split, two 32K transforms, radix-2 join: 28 B of traffic per
                                         sample) instead of on chip in a cluster of two CTAs exchanging through distributed shared
                                         memory; same results within fp32 rounding, for A/B timing */

@@ -436,3 +436,28 @@ def test_stream_scan_with_short_chunks_and_aggregate_levels(rom):
         assert np.abs(f.get_state()[0].astype(int) - st[0].astype(int)).max() <= 32
     finally:
         f.close()
+
+
+@pytest.mark.parametrize("n", [1024, 16384])
+def test_half_spectrum_host_transfer_rebuilds_identical_frames(n, rom):
+    """FRA_HOST_HALF_SPECTRUM: bins 0..N/2 + one bit per bin cross the link, the host completes the mirror;
+    byte-identical to the full transfer (silence, full-scale DC and full-range noise among the channels)."""
+    c = 5
+    rng = np.random.default_rng(n)
+    x = rng.integers(-32768, 32768, (c, n)).astype(np.int16)
+    x[1] = 0
+    x[2] = -32768
+    x[3] = g.tone_noise([3], n=n, seed=1)[0]
+    a, b = EmulFra(c, n), EmulFra(c, n, _abi.FRA_HOST_HALF_SPECTRUM)
+    try:
+        for mode in (0x00, 0xB1):
+            a.command(bytes([mode])); b.command(bytes([mode]))
+            fa = a.process(x, want=("frames", "mag"), host=True)
+            fb = b.process(x, want=("frames", "mag"), host=True)
+            assert np.array_equal(fa["frames"], fb["frames"]) and np.array_equal(fa["mag"], fb["mag"])
+        # a scale that can saturate falls back to the full transfer: still identical
+        fa = a.process(x, log2_scale=-6, want=("frames",), host=True)
+        fb = b.process(x, log2_scale=-6, want=("frames",), host=True)
+        assert np.array_equal(fa["frames"], fb["frames"])
+    finally:
+        a.close(); b.close()
