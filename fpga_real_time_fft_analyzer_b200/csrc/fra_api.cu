@@ -596,19 +596,29 @@ void mirror_frame_scalar(uint32_t *fr, const uint32_t *bits, int n, int j0, int 
 }
 
 #ifdef FRA_HAVE_AVX2_PATH
+// Eight words per step.  The blocks are chosen so that the STORES are 32-byte aligned (j = 1 mod 8: words
+// N-j-7 .. N-j start at a multiple of 8) and go out as non-temporal stores: the upper half is written once and
+// not read again here, and a regular store would first read every line it overwrites (the mirror is bound by
+// host memory bandwidth, which it shares with the DMA engines).  `bits` has one word of slack behind the last frame.
 __attribute__((target("avx2"))) void mirror_frame_avx2(uint32_t *fr, const uint32_t *bits, int n)
 {
     const int m = n / 2;
-    mirror_frame_scalar(fr, bits, n, 1, 8);
+    mirror_frame_scalar(fr, bits, n, 1, 9);
     const __m256i lo = _mm256_set1_epi32(0xFFFF), one = _mm256_set1_epi32(1);
     const __m256i sh = _mm256_setr_epi32(0, 1, 2, 3, 4, 5, 6, 7), rev = _mm256_setr_epi32(7, 6, 5, 4, 3, 2, 1, 0);
-    for (int j = 8; j < m; j += 8) {                                   // words j .. j+7 -> N-j-7 .. N-j
+    const bool aligned = (reinterpret_cast<uintptr_t>(fr) & 31u) == 0;
+    int j = 9;
+    for (; j + 8 <= m; j += 8) {                                       // words j .. j+7 -> N-j-7 .. N-j
         const __m256i w = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(fr + j));
-        const __m256i b = _mm256_and_si256(_mm256_srlv_epi32(_mm256_set1_epi32((int)((bits[j >> 5] >> (j & 31)) & 0xFFu)), sh), one);
+        uint64_t two;
+        std::memcpy(&two, bits + (j >> 5), sizeof(two));
+        const __m256i b = _mm256_and_si256(_mm256_srlv_epi32(_mm256_set1_epi32((int)((two >> (j & 31)) & 0xFFu)), sh), one);
         const __m256i hi = _mm256_add_epi32(_mm256_srli_epi32(_mm256_xor_si256(w, _mm256_set1_epi32(-1)), 16), _mm256_sub_epi32(one, b));
-        const __m256i r = _mm256_or_si256(_mm256_and_si256(w, lo), _mm256_slli_epi32(hi, 16));
-        _mm256_storeu_si256(reinterpret_cast<__m256i *>(fr + n - j - 7), _mm256_permutevar8x32_epi32(r, rev));
+        const __m256i r = _mm256_permutevar8x32_epi32(_mm256_or_si256(_mm256_and_si256(w, lo), _mm256_slli_epi32(hi, 16)), rev);
+        if (aligned) _mm256_stream_si256(reinterpret_cast<__m256i *>(fr + n - j - 7), r);
+        else _mm256_storeu_si256(reinterpret_cast<__m256i *>(fr + n - j - 7), r);
     }
+    mirror_frame_scalar(fr, bits, n, j, m);
 }
 #endif
 
@@ -632,6 +642,9 @@ void host_mirror(fra_ctx *ctx, int slot)
 #endif
             mirror_frame_scalar(fr, bits + f * words, n, 1, n / 2);
         }
+#ifdef FRA_HAVE_AVX2_PATH
+        _mm_sfence();                                                   // the non-temporal stores are visible before the join
+#endif
     };
     const size_t hw = std::max(1u, std::thread::hardware_concurrency());
     const size_t n_thr = std::min<size_t>(std::min<size_t>(hw, 32), std::max<size_t>(1, C * (size_t)n >> 20));
@@ -1094,7 +1107,7 @@ int fra_process_host_async(fra_ctx *ctx, const int16_t *h_in, int continuous, in
     if (half) {
         if (!need((void **)&ctx->d_mbits, C * mwords * 4)) return FRA_ERR_NOMEM;
         for (auto &hb : ctx->h_mbits)
-            if (!hb && cudaMallocHost((void **)&hb, C * mwords * 4) != cudaSuccess) return FRA_ERR_NOMEM;
+            if (!hb && cudaMallocHost((void **)&hb, C * mwords * 4 + 8) != cudaSuccess) return FRA_ERR_NOMEM;
     }
 
     fra_outputs dev;
