@@ -516,6 +516,7 @@ int process_range(fra_ctx *ctx, const int16_t *d_in, int c0, int nch, int contin
         k2.mag_alpha = ctx->mag_alpha;
         k2.batch = nch;
         k2.frame0 = c0;
+        k2.prefetch = ctx->sm_count * FRA_K2_MINBLOCKS;
 #ifdef FRA_TIMELINE
         k2.tl_step = (int)ctx->pipe_calls;
 #endif
@@ -1464,6 +1465,7 @@ int fra_fft_only(fra_ctx *ctx, const int16_t *d_in, int batch, float *d_iq, void
     k2.mag_alpha = 1.0f;
     k2.batch = batch;
     k2.frame0 = 0;
+    k2.prefetch = ctx->sm_count * FRA_K2_MINBLOCKS;
 #ifdef FRA_TIMELINE
     k2.tl_step = -1;
 #endif
