@@ -38,6 +38,7 @@ FRA_K2_STAGED = 0x100
 FRA_FFT_FIXED16 = 0x200
 FRA_K2_64K_SPLIT = 0x400
 FRA_HOST_HALF_SPECTRUM = 0x800
+FRA_WINDOW_RTL_SKEW = 0x1000
 
 
 class FraOutputs(C.Structure):

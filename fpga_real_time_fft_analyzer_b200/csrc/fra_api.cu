@@ -109,6 +109,8 @@ struct fra_ctx {
     size_t scratch_elems = 0;         // int16 elements allocated at d_scratch
     // FRA_HOST_HALF_SPECTRUM: mirror bits on the device, their pinned host copies per call slot, and the frames
     // (host pointer) of each slot that still wait for their upper half
+    int16_t *d_skew_in = nullptr;     // FRA_WINDOW_RTL_SKEW: the input delayed by one sample, [C][N]
+    int16_t *d_skew_prev = nullptr;   // ... and every channel's last sample of the previous frame
     uint32_t *d_mbits = nullptr;
     uint32_t *h_mbits[2] = {nullptr, nullptr};
     uint8_t *mirror_frames[2] = {nullptr, nullptr};
@@ -416,6 +418,19 @@ int process_range(fra_ctx *ctx, const int16_t *d_in, int c0, int nch, int contin
 {
     if (!scratch) scratch = ctx->d_scratch;
     const int n = ctx->n;
+    if (ctx->flags & FRA_WINDOW_RTL_SKEW) {
+        // the stream delayed by one sample (the ROM tables are rotated by two): out[n] = W(x[n-1], ROM[n-2])
+        int16_t *delayed = ctx->d_skew_in + (size_t)c0 * n;
+        int16_t *prev = ctx->d_skew_prev + c0;
+        const size_t total8 = (size_t)nch * n / 8;
+        auto dk = k0_skew_delay;
+        FRA_LAUNCH(dk, dim3((unsigned)((total8 + 255) / 256)), dim3(256), (size_t)0, st, d_in, delayed, prev, total8, n, continuous);
+        FRA_TRY(ctx, cudaGetLastError());
+        auto ck = k0_skew_carry;
+        FRA_LAUNCH(ck, dim3((unsigned)((nch + 255) / 256)), dim3(256), (size_t)0, st, d_in, prev, nch, n);
+        FRA_TRY(ctx, cudaGetLastError());
+        d_in = delayed;
+    }
     const bool iir = (ctx->mode == FRA_MODE_BANK0 || ctx->mode == FRA_MODE_BANK1);
     const bool want_fft = o.d_frames || o.d_iq || o.d_mag || o.d_phase;
     const int16_t *fft_in = d_in;
@@ -716,6 +731,7 @@ int fra_create(fra_ctx **out, int device, int n_channels, int fft_size, unsigned
     if ((1 << log2n) != fft_size) return FRA_ERR_INVALID;
     if (log2n < 10 || log2n > 16) return FRA_ERR_UNSUPPORTED;
     if ((flags & FRA_FFT_FIXED16) && log2n > 15) return FRA_ERR_UNSUPPORTED;      // the frame must fit one SM's shared memory
+    if ((flags & FRA_WINDOW_RTL_SKEW) && (flags & FRA_PIPELINE)) return FRA_ERR_UNSUPPORTED;   // one delayed-input buffer
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return FRA_ERR_NO_DEVICE;
     if (device < 0 || device >= count) return FRA_ERR_INVALID;
@@ -747,9 +763,10 @@ int fra_create(fra_ctx **out, int device, int n_channels, int fft_size, unsigned
     if (cudaMalloc((void **)&ctx->d_twn, (n_kernel / 2) * sizeof(float2)) != cudaSuccess) return bail(FRA_ERR_NOMEM);
 
     std::vector<int> rom32(kWindowLen), rom2x(kWindowLen);
+    const int rot = (flags & FRA_WINDOW_RTL_SKEW) ? 2 : 0;            // sample n-1 meets ROM[n-2] (hann8192.vhd:36-39)
     for (int i = 0; i < kWindowLen; ++i) {
-        rom32[i] = kHannRom[i];
-        rom2x[i] = 2 * kHannRom[i];
+        rom32[i] = kHannRom[(i - rot) & (kWindowLen - 1)];
+        rom2x[i] = 2 * rom32[i];
     }
     std::vector<float2> tw1(256), tw2(4096), twn(n_kernel / 2);
     const double two_pi = 6.283185307179586476925286766559;
@@ -784,6 +801,12 @@ int fra_create(fra_ctx **out, int device, int n_channels, int fft_size, unsigned
         cudaMemcpy(ctx->d_twn, twn.data(), twn.size() * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemset(ctx->d_state, 0, (size_t)n_channels * 24 * sizeof(int16_t)) != cudaSuccess)
         return bail(FRA_ERR_CUDA);
+    if (flags & FRA_WINDOW_RTL_SKEW) {
+        if (cudaMalloc((void **)&ctx->d_skew_in, (size_t)n_channels * n * sizeof(int16_t)) != cudaSuccess ||
+            cudaMalloc((void **)&ctx->d_skew_prev, (size_t)n_channels * sizeof(int16_t)) != cudaSuccess)
+            return bail(FRA_ERR_NOMEM);
+        if (cudaMemset(ctx->d_skew_prev, 0, (size_t)n_channels * sizeof(int16_t)) != cudaSuccess) return bail(FRA_ERR_CUDA);
+    }
     if (flags & FRA_FFT_FIXED16) {
         // phase factors of the fixed-point mode: round(cos, -sin * 2^15) clipped to 32767 (xfft_0.xci:19, 16 bits)
         std::vector<uint32_t> twfx(n);
@@ -835,7 +858,7 @@ int fra_destroy(fra_ctx *ctx)
         if (pe) cudaEventDestroy(pe);
     for (auto hb : ctx->h_mbits)
         if (hb) cudaFreeHost(hb);
-    void *bufs[] = {ctx->d_rom32, ctx->d_rom2x, ctx->d_twfx, ctx->d_mbits, ctx->d_state, ctx->d_scratch, ctx->d_tw1, ctx->d_tw2, ctx->d_twn, ctx->d_in, ctx->d_twc, ctx->d_halves, ctx->d_split,
+    void *bufs[] = {ctx->d_rom32, ctx->d_rom2x, ctx->d_twfx, ctx->d_mbits, ctx->d_skew_in, ctx->d_skew_prev, ctx->d_state, ctx->d_scratch, ctx->d_tw1, ctx->d_tw2, ctx->d_twn, ctx->d_in, ctx->d_twc, ctx->d_halves, ctx->d_split,
                     ctx->d_frames, ctx->d_filtered_out, ctx->d_iq, ctx->d_mag, ctx->d_phase, ctx->d_entry,
                     ctx->d_exit, ctx->d_counts, ctx->d_ends, ctx->d_aggr, ctx->d_mats};
     for (void *p : bufs)
@@ -934,6 +957,7 @@ int fra_reset(fra_ctx *ctx)
     FRA_TRY(ctx, host_streams_join(ctx));
     // synchronous: a reset must be ordered before work on ANY stream the caller uses next
     FRA_TRY(ctx, cudaMemsetAsync(ctx->d_state, 0, (size_t)ctx->channels * 24 * sizeof(int16_t), ctx->stream));
+    if (ctx->d_skew_prev) FRA_TRY(ctx, cudaMemsetAsync(ctx->d_skew_prev, 0, (size_t)ctx->channels * sizeof(int16_t), ctx->stream));
     FRA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return FRA_OK;
 }
@@ -1205,6 +1229,7 @@ int fra_iir_stream(fra_ctx *ctx, const int16_t *d_in, int16_t *d_out, size_t n, 
                    fra_stream_stats *stats)
 {
     if (!ctx || !d_in || !d_out || n == 0 || (n % 8) != 0) return FRA_ERR_INVALID;
+    if (ctx->flags & FRA_WINDOW_RTL_SKEW) return FRA_ERR_UNSUPPORTED;      // frames only
     FRA_TRY(ctx, cudaSetDevice(ctx->device));
     FRA_TRY(ctx, pipe_host_join(ctx));
     cudaStream_t st = ctx->stream;

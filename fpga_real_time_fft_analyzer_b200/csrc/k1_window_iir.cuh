@@ -956,6 +956,39 @@ __global__ void __launch_bounds__(kDuoWarps * 32, 2) k1_duo(K1Args a)
     }
 }
 
+// ------------------------------------------------- FRA_WINDOW_RTL_SKEW: the window's register skew
+// hann8192.vhd:36-39 updates coef_s, product and sample_out in the same clocked branch, so at strobe n the
+// output is the rounding of x[n-1] * ROM[n-2]; the first two outputs after power-up come from
+// zero registers.  In this mode the chain runs on the stream delayed by one sample (this kernel: the
+// previous frame's last sample is carried per channel) with the ROM tables rotated by two entries.
+__global__ void __launch_bounds__(256) k0_skew_delay(const int16_t *in, int16_t *out, int16_t *prev, size_t total8, int n,
+                                                      int continuous)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // one thread = 8 consecutive samples
+    if (i >= total8) return;
+    const size_t e = i * 8;
+    const size_t c = e / (size_t)n;
+    const int n0 = (int)(e % (size_t)n);
+    const uint4 x = ldg128(in + e);
+    // the sample in front of these eight: the previous group's last one, or the carry of the previous frame
+    unsigned before;
+    if (n0 == 0) before = continuous ? (unsigned)(uint16_t)prev[c] : 0u;
+    else before = (unsigned)(uint16_t)in[e - 1];
+    uint4 o;
+    o.x = (x.x << 16) | before;
+    o.y = (x.y << 16) | (x.x >> 16);
+    o.z = (x.z << 16) | (x.y >> 16);
+    o.w = (x.w << 16) | (x.z >> 16);
+    if (n0 == 0 && !continuous) o.x = 0u;            // power-up: x[0] meets the still-zero coefficient register
+    stg128(out + e, o);
+}
+
+__global__ void __launch_bounds__(256) k0_skew_carry(const int16_t *in, int16_t *prev, int channels, int n)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < channels) prev[c] = in[(size_t)c * n + n - 1];
+}
+
 // ------------------------------------------------------------ window only
 // Bypass mode with the FFT input stream requested as an output: the window
 // alone (in bypass the FFT kernel applies the window itself while loading).

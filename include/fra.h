@@ -79,6 +79,11 @@ typedef enum fra_status {
 #define FRA_K2_STAGED       0x100u   /* 16K frames: persistent FFT CTAs whose frames arrive by one bulk copy each (cp.async.bulk on an
                                         mbarrier) instead of one frame per CTA with per-thread loads; same results, measured
                                         slower on B200, kept for A/B timing */
+#define FRA_WINDOW_RTL_SKEW 0x1000u  /* the window with the register skew of the RTL as written (NEW/hann8192.vhd:36-39):
+                                        coef_s, product and sample_out update in one clocked branch, so output n is the rounding
+                                        of x[n-1] * ROM[n-2], and the first two outputs after a gap come from zero registers.
+                                        Default (flag clear) is the aligned window, y[n] = f(x[n], ROM[n]).  Frames only
+                                        (fra_iir_stream and FRA_PIPELINE return FRA_ERR_UNSUPPORTED). */
 #define FRA_HOST_HALF_SPECTRUM 0x800u /* fra_process_host[_async]: the int16 frames cross PCIe as bins 0..N/2 plus one bit per bin
                                         (33 KiB instead of 64 KiB per 16K frame) and fra_host_wait completes the Hermitian upper
                                         half on the host's cores - X[N-j] = {re, -im - bit}, the bit saying whether floor(-Im s)

@@ -93,6 +93,20 @@ def window(x: np.ndarray, rom: np.ndarray, start: int = 0) -> np.ndarray:
     return (low15 - (sign << 15)).astype(np.int16)
 
 
+def window_rtl_skew(x: np.ndarray, rom: np.ndarray, prev=None) -> np.ndarray:
+    """hann_window as WRITTEN (NEW/hann8192.vhd:36-39): coef_s, product and sample_out are
+    registers of the same clocked branch, so output n is the rounding of x[n-1] * ROM[n-2]; from zero
+    registers (prev is None: power-up) the first two outputs are 0.  ``prev`` = the sample in front of
+    x[..., 0] when the stream continues (then frame lengths must be multiples of the ROM length for the
+    free-running address to restart at 0).  x: int16 [..., T]."""
+    x = np.asarray(x)
+    lead = np.zeros(x.shape[:-1] + (1,), dtype=x.dtype) if prev is None else np.asarray(prev, dtype=x.dtype).reshape(x.shape[:-1] + (1,))
+    delayed = np.concatenate([lead, x[..., :-1]], axis=-1)
+    if prev is None:
+        delayed[..., :2] = 0
+    return window(delayed, np.roll(np.asarray(rom), 2))
+
+
 # --------------------------------------------------------------------------- a3
 def slice_T(v, c):
     """One product term of the biquad: mult(22 downto 7) of a 16x8->24-bit

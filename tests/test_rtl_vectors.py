@@ -107,3 +107,68 @@ def test_cuda_path_reproduces_the_vhdl_vectors(vec, key, variant):
         batch = np.repeat(x[-1][None], c, axis=0)
         got = ctx.process(torch.from_numpy(batch).cuda(), want=("filtered",))["filtered"].cpu().numpy()
         assert np.array_equal(got[5], win[-1])
+
+
+# ------------------------------------------------------------ the window exactly as the text clocks it
+@pytest.fixture(scope="module")
+def raw():
+    return np.load(os.path.join(ROOT, "tests", "golden", "rtl_window_raw.npz"))
+
+
+def test_window_register_skew_oracle(raw, rom):
+    """hann8192.vhd evaluated with NO stimulus compensation (sample n presented at strobe n, two frames from
+    power-up): output n = W(x[n-1], ROM[n-2]), the first two outputs 0."""
+    x, y = raw["x"], raw["y"]
+    assert np.array_equal(g.window_rtl_skew(x[0][None], rom)[0], y[0])
+    assert np.array_equal(g.window_rtl_skew(x[1][None], rom, prev=x[0][-1:])[0], y[1])
+    assert not y[0][:2].any() and not np.array_equal(y[0], g.window(x[0][None], rom)[0])
+
+
+def test_window_register_skew_mode_emulated(raw, rom):
+    from fpga_real_time_fft_analyzer_b200 import _abi
+    from tests.emul.emul_lib import EmulFra
+    x, y = raw["x"], raw["y"]
+    f = EmulFra(2, 16384, _abi.FRA_WINDOW_RTL_SKEW)
+    try:
+        for fr in range(2):                                   # bypass: the FFT input stream is the window's output
+            out = f.process(np.stack([x[fr], x[fr]]), continuous=fr > 0, want=("filtered",))["filtered"]
+            assert np.array_equal(out[1], y[fr]), fr
+        f.command(bytes([0x00]))                              # ... and the filter runs on that stream
+        out = f.process(np.stack([x[0], x[0]]), want=("filtered",))["filtered"]
+        want, _ = g.iir12(y[0][None], g.BANK0_COEFF)
+        assert np.array_equal(out[0], want[0])
+    finally:
+        f.close()
+
+
+@pytest.mark.gpu
+def test_window_register_skew_mode(raw, rom):
+    """FRA_WINDOW_RTL_SKEW on the GPU against the raw VHDL-evaluated window, two continuous frames, then through
+    the cascade (every K1 kernel the dispatcher can pick at this size) and the FFT."""
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.fail("-m gpu tests need a CUDA device; there is no CPU fallback")
+    from fpga_real_time_fft_analyzer_b200 import FraContext, FraError, _abi
+    x, y = raw["x"], raw["y"]
+    c = 40
+    for flags in (0, _abi.FRA_K1_FORCE_LANE, _abi.FRA_K1_FORCE_DUO):
+        with FraContext(c, 16384, flags=flags | _abi.FRA_WINDOW_RTL_SKEW) as ctx:
+            for fr in range(2):
+                batch = torch.from_numpy(np.repeat(x[fr][None], c, axis=0)).cuda()
+                out = ctx.process(batch, continuous=fr > 0, want=("filtered", "iq"))
+                assert np.array_equal(out["filtered"][c - 1].cpu().numpy(), y[fr]), (flags, fr)
+                iq = out["iq"][0].cpu().numpy()
+                ref = np.fft.fft(y[fr].astype(np.float64))
+                assert np.linalg.norm((iq[..., 0] + 1j * iq[..., 1]) - ref) / np.linalg.norm(ref) < 1e-4
+            ctx.command(0xFF)                                 # reset: power-up state again
+            ctx.command(0x00)
+            st = None
+            for fr in range(2):
+                batch = torch.from_numpy(np.repeat(x[fr][None], c, axis=0)).cuda()
+                got = ctx.process(batch, continuous=fr > 0, want=("filtered",))["filtered"][7].cpu().numpy()
+                want, st = g.iir12(y[fr][None], g.BANK0_COEFF, st)
+                assert np.array_equal(got, want[0]), (flags, fr)
+            with pytest.raises(FraError):
+                ctx.iir_stream(torch.zeros(4096, dtype=torch.int16, device="cuda"))
+    with pytest.raises(FraError):
+        FraContext(4, 16384, flags=_abi.FRA_WINDOW_RTL_SKEW | _abi.FRA_PIPELINE)
