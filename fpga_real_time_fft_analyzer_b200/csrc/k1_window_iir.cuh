@@ -171,10 +171,11 @@ FRA_DEV void window8_biased(uint4 x, int4 ra, int4 rb, unsigned exp23, float (&u
     u[4] = w(lo16(x.z), rb.x); u[5] = w(hi16(x.z), rb.y); u[6] = w(lo16(x.w), rb.z); u[7] = w(hi16(x.w), rb.w);
 }
 
-// ROM entries equal to -32768 live in [0, 15), [8178, 8206) and [16369, 16384): does [w0, w0 + len) touch one?
+// ROM entries equal to -32768 live in [0, 15), [8178, 8206) and [16369, 16384) - two entries later in the table
+// rotated for FRA_WINDOW_RTL_SKEW, so the ranges are taken two wider: does [w0, w0 + len) touch one?
 FRA_DEV bool rom_quirk_range(int w0, int len)
 {
-    return (w0 < 15) || (w0 + len > 8178 && w0 < 8206) || (w0 + len > 16369);
+    return (w0 < 17) || (w0 + len > 8178 && w0 < 8208) || (w0 + len > 16369);
 }
 
 // One iteration of the skewed cascade: stage s works on sample i - s, so the six stage steps of an

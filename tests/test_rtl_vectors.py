@@ -139,6 +139,14 @@ def test_window_register_skew_mode_emulated(raw, rom):
         assert np.array_equal(out[0], want[0])
     finally:
         f.close()
+    # the lane kernel's fast window path must know where the rotated table holds -32768
+    f = EmulFra(2, 16384, _abi.FRA_WINDOW_RTL_SKEW | _abi.FRA_K1_FORCE_LANE)
+    try:
+        f.command(bytes([0x00]))
+        out = f.process(np.stack([x[0], x[0]]), want=("filtered",))["filtered"]
+        assert np.array_equal(out[1], want[0])
+    finally:
+        f.close()
 
 
 @pytest.mark.gpu
