@@ -213,9 +213,18 @@ struct BinOut {
 // One bin and its conjugate-symmetric partner: X[up + off] = p/2, X[dn + off_conj] = conj(p)/2.
 // `up` / `dn` are element indices (frame base +k and frame base -k) computed once per work item,
 // `off` / `off_conj` are compile-time constants, so every store is base + immediate.
-template <int QMODE>
+// ONLY_FRAMES: the int16 frames are the only output and their pointer is known to be non-null (OUT = 0)
+template <int QMODE, bool ONLY_FRAMES = false>
 FRA_DEV void emit_pair(const BinOut &o, size_t up, size_t dn, int off, int off_conj, bool write_conj, float2 p)
 {
+    if (ONLY_FRAMES) {
+        const float qre = quant<QMODE>(p.x, o.qscale);
+        const float qim = quant<QMODE>(p.y, o.qscale);
+        const float qimc = quant<QMODE>(p.y, -o.qscale);
+        o.frames[up + off] = __byte_perm(__float_as_uint(qre), __float_as_uint(qim), 0x5410);
+        if (write_conj) o.frames[dn + off_conj] = __byte_perm(__float_as_uint(qre), __float_as_uint(qimc), 0x5410);
+        return;
+    }
     if (o.iq != nullptr) {
         o.iq[up + off] = make_float2(0.5f * p.x, 0.5f * p.y);
         if (write_conj) o.iq[dn + off_conj] = make_float2(0.5f * p.x, -0.5f * p.y);
@@ -387,6 +396,11 @@ FRA_DEV void fft_pass(const K2Args &a, float2 *buf, int tid, int frame0, const u
     __syncthreads();
 }
 
+template <bool B>
+struct BoolTag {
+    static constexpr bool value = B;
+};
+
 // OUT = 0: int16 frames only (the hot configuration); OUT = 1: any combination of
 // outputs, selected at run time by the null pointers in K2Args.
 // the last pass of the CTA's frames [frame0, frame0 + FPC): radix-F combine, untangle, mirror, pack.
@@ -404,13 +418,16 @@ FRA_DEV void fft_last_pass(const K2Args &a, const float2 *buf, int tid, int fram
     out.phase = (OUT == 0) ? nullptr : a.phase;
     out.mag_alpha = a.mag_alpha;
 
-    // one work item: the pair of sub-FFT bins (k, L-k) of frame `fr`, all F sub-sequences
-    auto item = [&](int fr, int k, float2 wn) {
+    // one work item: the pair of sub-FFT bins (k, L-k) of frame `fr`, all F sub-sequences.
+    // MAIN (a std::true_type-like tag): 0 < k < L/2, so every bin has its mirror partner and is written once; `sk` /
+    // `skm` = swz(k) / swz(L - k) then come from the caller (they advance by the item stride, see below)
+    auto item = [&](auto main_tag, int fr, int k, float2 wn, int sk_in, int skm_in) {
+        constexpr bool MAIN = decltype(main_tag)::value;
         const int frame = frame0 + fr;
         const size_t up = (size_t)frame * P::N + k;
         const size_t dn = (size_t)frame * P::N - k;
         const int km = (P::L - k) & (P::L - 1);
-        const int sk = swz(k), skm = swz(km);                          // f L is a multiple of 8 rows
+        const int sk = MAIN ? sk_in : swz(k), skm = MAIN ? skm_in : swz(km);   // f L is a multiple of 8 rows
         float2 za[P::F], zb[P::F];
 #pragma unroll
         for (int f = 0; f < P::F; ++f) {
@@ -467,34 +484,58 @@ FRA_DEV void fft_last_pass(const K2Args &a, const float2 *buf, int tid, int fram
             // M - j = j'); both writers run in this thread and the mirrored one keeps X[N - k] =
             // conj(X[k]) bit-exact, so both are kept - except when the magnitude output averages,
             // which is a read-modify-write and must touch every bin exactly once
-            const bool once = out.mag_alpha < 1.0f && (k == 0 || k == P::L / 2);
-            emit_pair<QMODE>(out, up, dn, P::L * q, P::N - P::L * q, !once && ((q > 0) || (k != 0)), p);
-            emit_pair<QMODE>(out, up, dn, P::M + P::L * q, P::M - P::L * q, !once, m);
+            const bool once = !MAIN && out.mag_alpha < 1.0f && (k == 0 || k == P::L / 2);
+            emit_pair<QMODE, OUT == 0>(out, up, dn, P::L * q, P::N - P::L * q, MAIN || (!once && ((q > 0) || (k != 0))), p);
+            emit_pair<QMODE, OUT == 0>(out, up, dn, P::M + P::L * q, P::M - P::L * q, MAIN || !once, m);
         }
     };
+    using TagMain = BoolTag<true>;
+    using TagEdge = BoolTag<false>;
 
-    // k = 1 .. L/2 - 1: uniform work; the twiddle of the next item is fetched one item ahead
-    // (in a cluster the two CTAs take alternate blocks of THREADS items)
+    // k = 1 .. L/2 - 1: uniform work (in a cluster the two CTAs take alternate blocks of THREADS items).  The trip
+    // count is a compile-time constant and the loop is unrolled: the item stride is a multiple of 128 elements, which
+    // leaves the swizzle's row bits alone - swz(k + i STEP) = swz(k) + i STEP, swz(L - k - i STEP) = swz(L - k) - i STEP -
+    // so shared-memory addresses, the twiddle address and all eight store addresses of an item are one base register
+    // plus an immediate (the rolled loop spent 30 of its 100 instructions per item on addresses, bounds and branches).
     {
-        constexpr int SLOTS = P::FPC * (P::L / 2);
+        constexpr int HALF = P::L / 2;
+        constexpr int SLOTS = P::FPC * HALF;
         constexpr int STEP = CLUSTER ? 2 * P::THREADS : P::THREADS;
-        int slot = tid + (CLUSTER ? rank * P::THREADS : 0);
-        float2 wn_next = __ldg(a.twn + (slot % (P::L / 2)));
-#pragma unroll 1
-        for (; slot < SLOTS; slot += STEP) {
-            const int fr = slot / (P::L / 2);
-            const int k = slot % (P::L / 2);
-            const float2 wn = wn_next;
-            const int nslot = slot + STEP;
-            if (nslot < SLOTS) wn_next = __ldg(a.twn + (nslot % (P::L / 2)));
-            if (k != 0 && frame0 + fr < a.batch) item(fr, k, wn);
+        constexpr int TRIPS = SLOTS / STEP;
+        static_assert(SLOTS % STEP == 0 && STEP % 128 == 0, "last pass: whole trips, swizzle-preserving stride");
+        const int slot0 = tid + (CLUSTER ? rank * P::THREADS : 0);
+        if constexpr (STEP <= HALF) {
+            // one frame per CTA (FPC = 1 whenever L = 4096 ... or two frames of 8K): k advances, the frame is fixed per trip
+            static_assert(HALF % STEP == 0, "last pass: trips per frame");
+            const int k0 = slot0 % HALF;
+            const int sk0 = swz(k0), skm0 = swz(P::L - k0);           // (k0 = 0: L itself, so that L - ii follows from it)
+#pragma unroll
+            for (int i = 0; i < TRIPS; ++i) {
+                const int fr = (i * STEP) / HALF;
+                const int ii = (i * STEP) % HALF;                        // compile-time offset of k within the frame
+                const int k = k0 + ii;
+                const bool live = (P::FPC == 1) || (frame0 + fr < a.batch);
+                if ((ii > 0 || k0 != 0) && live)
+                    item(TagMain(), fr, k, __ldg(a.twn + k), sk0 + ii, skm0 - ii);
+            }
+        } else {
+            // several frames per trip (L = 256): k is fixed per thread, the frame advances
+            static_assert(STEP % HALF == 0, "last pass: frames per trip");
+            const int k = slot0 % HALF;
+            const int sk = swz(k), skm = swz((P::L - k) & (P::L - 1));
+            const float2 wn = __ldg(a.twn + k);
+#pragma unroll
+            for (int i = 0; i < TRIPS; ++i) {
+                const int fr = slot0 / HALF + i * (STEP / HALF);
+                if (k != 0 && frame0 + fr < a.batch) item(TagMain(), fr, k, wn, sk, skm);
+            }
         }
     }
     // the two self-paired items k = 0 and k = L/2 of every frame in the CTA (in a cluster: one each)
     if (tid < 2 * P::FPC && (!CLUSTER || (tid & 1) == rank)) {
         const int fr = tid >> 1;
         const int k = (tid & 1) ? (P::L / 2) : 0;
-        if (frame0 + fr < a.batch) item(fr, k, __ldg(a.twn + k));
+        if (frame0 + fr < a.batch) item(TagEdge(), fr, k, __ldg(a.twn + k), 0, 0);
     }
 }
 
