@@ -74,6 +74,9 @@ SIGNATURES = {
     "fra_process_host_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(FraOutputs),
                                          C.POINTER(C.c_uint64)]),
     "fra_host_wait": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "fra_set_host_half_share": (C.c_int, [C.c_void_p, C.c_double]),
+    "fra_get_host_transfer": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_double),
+                                        C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "fra_get_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "fra_set_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "fra_iir_stream": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int,

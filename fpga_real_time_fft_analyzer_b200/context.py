@@ -227,6 +227,19 @@ class FraContext:
     def host_wait(self, ticket):
         self._check(self._L.fra_host_wait(self._h, C.c_uint64(int(ticket))), "fra_host_wait")
 
+    def set_host_half_share(self, share=-1.0):
+        """FRA_HOST_HALF_SPECTRUM: share of the frames sent as half spectra, 0..1; negative = adaptive (default)."""
+        self._check(self._L.fra_set_host_half_share(self._h, C.c_double(float(share))), "fra_set_host_half_share")
+
+    def host_transfer(self):
+        """(h2d_bytes, d2h_bytes) of the last host call and the half-spectrum share the next one will use."""
+        h2d, d2h, share = C.c_uint64(0), C.c_uint64(0), C.c_double(0.0)
+        wait, mirror = C.c_double(0.0), C.c_double(0.0)
+        self._check(self._L.fra_get_host_transfer(self._h, C.byref(h2d), C.byref(d2h), C.byref(share), C.byref(wait),
+                                                  C.byref(mirror)), "fra_get_host_transfer")
+        self.host_wait_s, self.host_mirror_s = wait.value, mirror.value
+        return h2d.value, d2h.value, share.value
+
     def get_state(self):
         torch = _torch()
         st = torch.empty((self.channels, 6, 4), dtype=torch.int16, device=f"cuda:{self.device}")

@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <new>
 #include <thread>
@@ -113,7 +114,21 @@ struct fra_ctx {
     int16_t *d_skew_prev = nullptr;   // ... and every channel's last sample of the previous frame
     uint32_t *d_mbits = nullptr;
     uint32_t *h_mbits[2] = {nullptr, nullptr};
-    uint8_t *mirror_frames[2] = {nullptr, nullptr};
+    // the frames of each call slot that still wait for their upper half: in every channel slice [s per, s per + per)
+    // the first nh[s] frames crossed the link as half spectra
+    struct MirrorPlan {
+        uint8_t *frames = nullptr;
+        size_t per = 0, nh[8] = {0};
+        int n_slices = 0;
+    } mirror_plan[2];
+    // share of the frames that travel as half spectra: the rest go whole, so that the link (DMA) and the host's
+    // cores (mirror) finish together.  Adapted per call from the time fra_host_wait spent waiting for the copies
+    // against the time it spent mirroring; half_step halves at every reversal.
+    double half_frac = 1.0, half_step = 0.125;
+    int half_dir = 0;
+    bool half_adaptive = true;
+    uint64_t last_h2d_bytes = 0, last_d2h_bytes = 0;
+    double last_wait_s = 0.0, last_mirror_s = 0.0;   // of the newest finished call: blocked on its copies / mirroring
 
     bool profiling = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // K1 begin/end, K2 begin/end
@@ -590,7 +605,7 @@ cudaError_t pipe_host_join(fra_ctx *ctx)
 }
 
 // host waits for the copy streams (calls of fra_process_host_async still in flight)
-void host_mirror(fra_ctx *ctx, int slot);
+size_t host_mirror(fra_ctx *ctx, int slot);
 
 cudaError_t host_streams_join(fra_ctx *ctx)
 {
@@ -638,20 +653,32 @@ __attribute__((target("avx2"))) void mirror_frame_avx2(uint32_t *fr, const uint3
 }
 #endif
 
-// all frames of one call slot, the frames split over the host's threads
-void host_mirror(fra_ctx *ctx, int slot)
+// all half-spectrum frames of one call slot, split over the host's threads; returns how many there were
+size_t host_mirror(fra_ctx *ctx, int slot)
 {
-    uint8_t *base = ctx->mirror_frames[slot];
-    if (!base) return;
-    ctx->mirror_frames[slot] = nullptr;
+    fra_ctx::MirrorPlan plan = ctx->mirror_plan[slot];
+    if (!plan.frames) return 0;
+    ctx->mirror_plan[slot].frames = nullptr;
+    uint8_t *base = plan.frames;
     const int n = ctx->n, words = n / 64;                              // N/2 bits per frame
-    const size_t C = (size_t)ctx->channels;
     const uint32_t *bits = ctx->h_mbits[slot];
 #ifdef FRA_HAVE_AVX2_PATH
     const bool avx2 = __builtin_cpu_supports("avx2");
 #endif
-    auto work = [&](size_t f0, size_t f1) {
-        for (size_t f = f0; f < f1; ++f) {
+    size_t total = 0;
+    for (int s = 0; s < plan.n_slices; ++s) total += plan.nh[s];
+    if (total == 0) return 0;
+    // the i-th half-spectrum frame of the call -> its channel
+    auto channel_of = [&](size_t i) {
+        for (int s = 0; s < plan.n_slices; ++s) {
+            if (i < plan.nh[s]) return (size_t)s * plan.per + i;
+            i -= plan.nh[s];
+        }
+        return (size_t)0;
+    };
+    auto work = [&](size_t i0, size_t i1) {
+        for (size_t i = i0; i < i1; ++i) {
+            const size_t f = channel_of(i);
             uint32_t *fr = reinterpret_cast<uint32_t *>(base + f * (size_t)n * 4);
 #ifdef FRA_HAVE_AVX2_PATH
             if (avx2) { mirror_frame_avx2(fr, bits + f * words, n); continue; }
@@ -662,24 +689,53 @@ void host_mirror(fra_ctx *ctx, int slot)
         _mm_sfence();                                                   // the non-temporal stores are visible before the join
 #endif
     };
-    const size_t hw = std::max(1u, std::thread::hardware_concurrency());
-    const size_t n_thr = std::min<size_t>(std::min<size_t>(hw, 32), std::max<size_t>(1, C * (size_t)n >> 20));
-    if (n_thr <= 1) { work(0, C); return; }
+    // threads: the host's hardware threads (at most 32), or FRA_HOST_THREADS when several processes share the host
+    size_t hw = std::max(1u, std::thread::hardware_concurrency());
+    if (const char *env = std::getenv("FRA_HOST_THREADS")) {
+        const long v = std::strtol(env, nullptr, 10);
+        if (v >= 1) hw = (size_t)v;
+    }
+    const size_t n_thr = std::min<size_t>(std::min<size_t>(hw, 32), std::max<size_t>(1, total * (size_t)n >> 20));
+    if (n_thr <= 1) { work(0, total); return total; }
     std::vector<std::thread> pool;
-    const size_t per = (C + n_thr - 1) / n_thr;
+    const size_t per = (total + n_thr - 1) / n_thr;
     for (size_t t = 0; t < n_thr; ++t) {
-        const size_t f0 = t * per, f1 = std::min(C, f0 + per);
-        if (f0 < f1) pool.emplace_back(work, f0, f1);
+        const size_t i0 = t * per, i1 = std::min(total, i0 + per);
+        if (i0 < i1) pool.emplace_back(work, i0, i1);
     }
     for (auto &th : pool) th.join();
+    return total;
 }
 
 // everything an earlier call left in slot `slot`: its copies have landed, its frames are whole
 int finish_host_slot(fra_ctx *ctx, int slot)
 {
+    using clk = std::chrono::steady_clock;
+    const bool pending = ctx->mirror_plan[slot].frames != nullptr;
+    const auto t0 = clk::now();
     for (cudaEvent_t e : ctx->host_done[slot])
         if (e) FRA_TRY(ctx, cudaEventSynchronize(e));
-    host_mirror(ctx, slot);
+    const auto t1 = clk::now();
+    const size_t mirrored = host_mirror(ctx, slot);
+    const auto t2 = clk::now();
+    // Balance the link against the mirror (steady state of a two-calls-in-flight loop): waiting for the copies
+    // means the link is the longer side -> more half spectra; no wait at all means the mirror is -> fewer.
+    const double wait = std::chrono::duration<double>(t1 - t0).count();
+    const double mir = std::chrono::duration<double>(t2 - t1).count();
+    if (pending) {
+        ctx->last_wait_s = wait;
+        ctx->last_mirror_s = mir;
+    }
+    if (pending && ctx->half_adaptive && ctx->host_calls >= 3) {
+        int dir = 0;
+        if (wait > 0.10 * (wait + mir)) dir = +1;
+        else if (wait < 0.02 * (wait + mir) && mirrored > 0) dir = -1;
+        if (dir != 0) {
+            if (ctx->half_dir != 0 && dir != ctx->half_dir) ctx->half_step = std::max(1.0 / 64.0, ctx->half_step * 0.5);
+            ctx->half_dir = dir;
+            ctx->half_frac = std::min(1.0, std::max(0.0, ctx->half_frac + dir * ctx->half_step));
+        }
+    }
     return FRA_OK;
 }
 
@@ -932,6 +988,28 @@ int fra_set_mag_average(fra_ctx *ctx, float alpha)
     return FRA_OK;
 }
 
+int fra_set_host_half_share(fra_ctx *ctx, double share)
+{
+    if (!ctx || share > 1.0) return FRA_ERR_INVALID;
+    ctx->half_adaptive = share < 0.0;
+    ctx->half_frac = share < 0.0 ? 1.0 : share;
+    ctx->half_step = 0.125;
+    ctx->half_dir = 0;
+    return FRA_OK;
+}
+
+int fra_get_host_transfer(const fra_ctx *ctx, uint64_t *h2d_bytes, uint64_t *d2h_bytes, double *half_share, double *wait_s,
+                          double *mirror_s)
+{
+    if (!ctx) return FRA_ERR_INVALID;
+    if (h2d_bytes) *h2d_bytes = ctx->last_h2d_bytes;
+    if (d2h_bytes) *d2h_bytes = ctx->last_d2h_bytes;
+    if (half_share) *half_share = ctx->half_frac;
+    if (wait_s) *wait_s = ctx->last_wait_s;
+    if (mirror_s) *mirror_s = ctx->last_mirror_s;
+    return FRA_OK;
+}
+
 int fra_get_sections(const fra_ctx *ctx, int8_t coeff[36])
 {
     if (!ctx || !coeff) return FRA_ERR_INVALID;
@@ -1151,6 +1229,12 @@ int fra_process_host_async(fra_ctx *ctx, const int16_t *h_in, int continuous, in
     const int n_slices = (int)std::min<size_t>(C, C * n >= ((size_t)1 << 24) ? 8 : 1);
     const size_t per = (C + n_slices - 1) / n_slices;
     int rc = FRA_OK;
+    fra_ctx::MirrorPlan plan;
+    plan.frames = h_out->d_frames;
+    plan.per = per;
+    plan.n_slices = n_slices;
+    const double half_frac = ctx->half_frac;
+    uint64_t d2h = 0;
     for (int s = 0; s < n_slices && rc == FRA_OK; ++s) {
         const size_t c0 = (size_t)s * per;
         if (c0 >= C) break;
@@ -1160,30 +1244,51 @@ int fra_process_host_async(fra_ctx *ctx, const int16_t *h_in, int continuous, in
         fra_outputs o = offset_outputs(dev, c0, (int)n);
         rc = process_range(ctx, ctx->d_in + c0 * n, (int)c0, (int)nch, continuous, log2_scale, o, st);
         if (rc != FRA_OK) break;
-        if (h_out->d_filtered)
+        if (h_out->d_filtered) {
             FRA_TRY(ctx, cudaMemcpyAsync(h_out->d_filtered + c0 * n, o.d_filtered, nch * n * 2, cudaMemcpyDeviceToHost, st));
+            d2h += nch * n * 2;
+        }
         if (h_out->d_frames && half) {
-            // bins 0 .. N/2 of every frame straight into the caller's frames (a pitched copy), the mirror bits
-            // into the slot's staging; fra_host_wait completes the upper halves on the host's cores
-            const size_t total = nch * (n / 2);
-            auto kfn = k3_mirror_bits;
-            int log2m = ctx->log2n - 1;
-            FRA_LAUNCH(kfn, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)0, st,
-                       (const uint32_t *)o.d_frames, ctx->d_mbits + c0 * mwords, total, log2m);
-            FRA_TRY(ctx, cudaGetLastError());
-            ctx->last_kernels++;
-            FRA_TRY(ctx, cudaMemcpy2DAsync(h_out->d_frames + c0 * n * 4, n * 4, o.d_frames, n * 4, (n / 2 + 1) * 4, nch,
-                                           cudaMemcpyDeviceToHost, st));
-            FRA_TRY(ctx, cudaMemcpyAsync(ctx->h_mbits[id & 1] + c0 * mwords, ctx->d_mbits + c0 * mwords, nch * mwords * 4,
-                                         cudaMemcpyDeviceToHost, st));
-        } else if (h_out->d_frames)
+            // the first nh frames of the slice: bins 0 .. N/2 straight into the caller's frames (a pitched copy), the
+            // mirror bits into the slot's staging; fra_host_wait completes the upper halves on the host's cores.
+            // The other frames of the slice cross the link whole.
+            const size_t nh = std::min(nch, (size_t)std::llround((double)nch * half_frac));
+            plan.nh[s] = nh;
+            if (nh > 0) {
+                const size_t total = nh * (n / 2);
+                auto kfn = k3_mirror_bits;
+                int log2m = ctx->log2n - 1;
+                FRA_LAUNCH(kfn, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)0, st,
+                           (const uint32_t *)o.d_frames, ctx->d_mbits + c0 * mwords, total, log2m);
+                FRA_TRY(ctx, cudaGetLastError());
+                ctx->last_kernels++;
+                FRA_TRY(ctx, cudaMemcpy2DAsync(h_out->d_frames + c0 * n * 4, n * 4, o.d_frames, n * 4, (n / 2 + 1) * 4, nh,
+                                               cudaMemcpyDeviceToHost, st));
+                FRA_TRY(ctx, cudaMemcpyAsync(ctx->h_mbits[id & 1] + c0 * mwords, ctx->d_mbits + c0 * mwords, nh * mwords * 4,
+                                             cudaMemcpyDeviceToHost, st));
+                d2h += nh * ((n / 2 + 1) * 4 + mwords * 4);
+            }
+            if (nh < nch) {
+                FRA_TRY(ctx, cudaMemcpyAsync(h_out->d_frames + (c0 + nh) * n * 4, o.d_frames + nh * n * 4, (nch - nh) * n * 4,
+                                             cudaMemcpyDeviceToHost, st));
+                d2h += (nch - nh) * n * 4;
+            }
+        } else if (h_out->d_frames) {
             FRA_TRY(ctx, cudaMemcpyAsync(h_out->d_frames + c0 * n * 4, o.d_frames, nch * n * 4, cudaMemcpyDeviceToHost, st));
-        if (h_out->d_iq)
+            d2h += nch * n * 4;
+        }
+        if (h_out->d_iq) {
             FRA_TRY(ctx, cudaMemcpyAsync(h_out->d_iq + c0 * n * 2, o.d_iq, nch * n * 8, cudaMemcpyDeviceToHost, st));
-        if (h_out->d_mag)
+            d2h += nch * n * 8;
+        }
+        if (h_out->d_mag) {
             FRA_TRY(ctx, cudaMemcpyAsync(h_out->d_mag + c0 * n, o.d_mag, nch * n * 4, cudaMemcpyDeviceToHost, st));
-        if (h_out->d_phase)
+            d2h += nch * n * 4;
+        }
+        if (h_out->d_phase) {
             FRA_TRY(ctx, cudaMemcpyAsync(h_out->d_phase + c0 * n, o.d_phase, nch * n * 4, cudaMemcpyDeviceToHost, st));
+            d2h += nch * n * 4;
+        }
     }
     if (rc != FRA_OK) {
         host_streams_join(ctx);
@@ -1195,7 +1300,9 @@ int fra_process_host_async(fra_ctx *ctx, const int16_t *h_in, int continuous, in
         if (!e) FRA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         FRA_TRY(ctx, cudaEventRecord(e, ctx->copy_streams[s]));
     }
-    if (half) ctx->mirror_frames[id & 1] = h_out->d_frames;
+    if (half) ctx->mirror_plan[id & 1] = plan;
+    ctx->last_h2d_bytes = (uint64_t)(C * n * 2);
+    ctx->last_d2h_bytes = d2h;
     ctx->host_calls = id;
     *ticket = id;
     return FRA_OK;

@@ -194,6 +194,18 @@ int fra_process_host_async(fra_ctx *ctx, const int16_t *h_in, int continuous, in
                            const struct fra_outputs *h_out, uint64_t *ticket);
 int fra_host_wait(fra_ctx *ctx, uint64_t ticket);
 
+/* FRA_HOST_HALF_SPECTRUM contexts: the share of a call's frames that cross the link as half spectra (the rest go
+ * whole, so that the DMA engines and the host cores that complete the mirror finish together).  share in [0, 1]
+ * fixes it; a negative value (the default) lets fra_host_wait adapt it from call to call: time spent waiting for
+ * the copies means the link is the longer side (more half spectra), no wait means the mirror is (fewer).
+ * fra_get_host_transfer reports the bytes the last fra_process_host[_async] call moved each way, the share the
+ * next call will use, and for the newest half-spectrum call that fra_host_wait finished how long it was blocked on
+ * the copies and how long the mirror took (seconds; any pointer may be NULL).  The frames are byte-identical
+ * whatever the share. */
+int fra_set_host_half_share(fra_ctx *ctx, double share);
+int fra_get_host_transfer(const fra_ctx *ctx, uint64_t *h2d_bytes, uint64_t *d2h_bytes, double *half_share, double *wait_s,
+                          double *mirror_s);
+
 /* IIR history, [C][6][4] int16 = per stage (x[n-1], x[n-2], y[n-1], y[n-2])
  * (registers ve(1..2), vs(1..2) of NEW/filter_iir_cust.vhd:45-46). Device pointers. */
 int fra_get_state(fra_ctx *ctx, int16_t *d_state, void *cuda_stream);

@@ -602,3 +602,31 @@ def test_half_spectrum_host_transfer(fra, rom, n, c):
         a = full.process_host(xs[0], log2_scale=-6, want=("frames",))["frames"].clone()
         b = half.process_host(xs[0], log2_scale=-6, want=("frames",))["frames"]
         assert torch.equal(a, b)
+        # mixed transfer: a fixed share of every channel slice as half spectra, the rest whole - same bytes out,
+        # and the bytes that crossed the link are what the share says
+        ref = full.process_host(xs[1], continuous=True, want=("frames",))["frames"].clone()
+        st = full.get_state().clone()
+        state0 = half.get_state().clone()
+        full_bytes = c * n * 4
+        for share in (0.0, 0.3, 0.77, 1.0):
+            half.set_host_half_share(share)
+            half.set_state(state0)
+            got = half.process_host(xs[1], continuous=True, want=("frames",))["frames"]
+            assert torch.equal(got, ref), share
+            assert torch.equal(half.get_state(), st)
+            h2d, d2h, sh = half.host_transfer()
+            assert h2d == c * n * 2 and sh == share
+            assert d2h <= full_bytes and (share > 0.0 or d2h == full_bytes) and (share < 1.0 or d2h < 0.53 * full_bytes)
+        # adaptive again (the default): whatever share the controller picks, the frames stay the same
+        half.set_host_half_share(-1.0)
+        ref0 = full.process_host(xs[2], continuous=False, want=("frames",))["frames"].clone()
+        pending = None
+        for i in range(8):
+            cur = half.process_host_async(xs[2], continuous=False, want=("frames",))
+            if pending is not None:
+                half.host_wait(pending[1])
+                assert torch.equal(pending[0]["frames"], ref0), i
+            pending = cur
+        half.host_wait(pending[1])
+        assert torch.equal(pending[0]["frames"], ref0)
+        assert 0.0 <= half.host_transfer()[2] <= 1.0
