@@ -329,14 +329,16 @@ def run_ours(args):
     # and a kernel's own span is not its cost)
     # The e2e context may send frames as bins 0..N/2 + one bit per bin and complete the Hermitian half on the host
     # (FRA_HOST_HALF_SPECTRUM: byte-identical frames, 2.06 instead of 4 B per sample device-to-host).  The library
-    # adapts the SHARE of frames sent that way from call to call so that the link and the host's cores finish
-    # together: one rank on a host settles near 3/4, eight ranks sharing one host's cores and memory go to full
-    # frames.  The warm-up loop below gives it its steps; the bytes reported are the ones actually moved.
-    # FRA_BENCH_HALF=0 switches the mode off.
+    # completes the upper halves slice by slice while the later slices still cross the link, and can send a share
+    # of the frames whole (adapted from the wait / mirror split; it stays at 1 on the hosts measured).  Used when at
+    # most two ranks share the host: the mirror costs host memory bandwidth (8 instead of 6 B per sample), and with
+    # eight ranks on one host that is the bottleneck, not the links (tools/e2e_probe_multi.sh, profiles/r02_e2e_*:
+    # full frames 34, adaptive 25, all-half 19 Gsamples/s over eight GPUs).  FRA_BENCH_HALF=0/1 overrides.
+    # The bytes reported are the ones actually moved.
     # the mirror's host threads: this rank's share of the host's cores (all ranks of the job share one host)
     os.environ.setdefault("FRA_HOST_THREADS", str(max(1, (os.cpu_count() or 1) // world)))
     half_env = os.environ.get("FRA_BENCH_HALF")
-    use_half = True if half_env is None else (half_env == "1")
+    use_half = (world <= 2) if half_env is None else (half_env == "1")
     seq = FraContext(channels, N, device=local, flags=_abi.FRA_HOST_HALF_SPECTRUM if use_half else 0)
     seq.command(0x00)
     seq.profile(True)

@@ -12,6 +12,7 @@
 #include "k2_fixed.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -128,6 +129,7 @@ struct fra_ctx {
     int half_dir = 0;
     bool half_adaptive = true;
     uint64_t last_h2d_bytes = 0, last_d2h_bytes = 0;
+    cudaEvent_t slice_done[2][8] = {{nullptr}};      // per call slot and channel slice: its device-to-host copies
     double last_wait_s = 0.0, last_mirror_s = 0.0;   // of the newest finished call: blocked on its copies / mirroring
 
     bool profiling = false;
@@ -605,7 +607,7 @@ cudaError_t pipe_host_join(fra_ctx *ctx)
 }
 
 // host waits for the copy streams (calls of fra_process_host_async still in flight)
-size_t host_mirror(fra_ctx *ctx, int slot);
+size_t host_mirror(fra_ctx *ctx, int slot, double *wait_s);
 
 cudaError_t host_streams_join(fra_ctx *ctx)
 {
@@ -613,7 +615,7 @@ cudaError_t host_streams_join(fra_ctx *ctx)
     for (auto st : ctx->copy_streams)
         if (st && e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e == cudaSuccess)
-        for (int slot = 0; slot < 2; ++slot) host_mirror(ctx, slot);   // frames of half-spectrum calls nobody waited for
+        for (int slot = 0; slot < 2; ++slot) host_mirror(ctx, slot, nullptr);   // frames of half-spectrum calls nobody waited for
     return e;
 }
 
@@ -653,10 +655,16 @@ __attribute__((target("avx2"))) void mirror_frame_avx2(uint32_t *fr, const uint3
 }
 #endif
 
-// all half-spectrum frames of one call slot, split over the host's threads; returns how many there were
-size_t host_mirror(fra_ctx *ctx, int slot)
+// All half-spectrum frames of one call slot.  The call's channel slices land one after the other (their copies are
+// queued in slice order), so the mirror is pipelined with the link: the calling thread waits for slice s's copies
+// (its event) and releases it to the worker threads, which each complete their part of every slice - the first
+// slices are mirrored while the last ones still cross the link.  Returns the number of frames mirrored;
+// *wait_s = how long the calling thread was blocked on copies.
+size_t host_mirror(fra_ctx *ctx, int slot, double *wait_s = nullptr)
 {
+    using clk = std::chrono::steady_clock;
     fra_ctx::MirrorPlan plan = ctx->mirror_plan[slot];
+    if (wait_s) *wait_s = 0.0;
     if (!plan.frames) return 0;
     ctx->mirror_plan[slot].frames = nullptr;
     uint8_t *base = plan.frames;
@@ -668,27 +676,6 @@ size_t host_mirror(fra_ctx *ctx, int slot)
     size_t total = 0;
     for (int s = 0; s < plan.n_slices; ++s) total += plan.nh[s];
     if (total == 0) return 0;
-    // the i-th half-spectrum frame of the call -> its channel
-    auto channel_of = [&](size_t i) {
-        for (int s = 0; s < plan.n_slices; ++s) {
-            if (i < plan.nh[s]) return (size_t)s * plan.per + i;
-            i -= plan.nh[s];
-        }
-        return (size_t)0;
-    };
-    auto work = [&](size_t i0, size_t i1) {
-        for (size_t i = i0; i < i1; ++i) {
-            const size_t f = channel_of(i);
-            uint32_t *fr = reinterpret_cast<uint32_t *>(base + f * (size_t)n * 4);
-#ifdef FRA_HAVE_AVX2_PATH
-            if (avx2) { mirror_frame_avx2(fr, bits + f * words, n); continue; }
-#endif
-            mirror_frame_scalar(fr, bits + f * words, n, 1, n / 2);
-        }
-#ifdef FRA_HAVE_AVX2_PATH
-        _mm_sfence();                                                   // the non-temporal stores are visible before the join
-#endif
-    };
     // threads: the host's hardware threads (at most 32), or FRA_HOST_THREADS when several processes share the host
     size_t hw = std::max(1u, std::thread::hardware_concurrency());
     if (const char *env = std::getenv("FRA_HOST_THREADS")) {
@@ -696,14 +683,40 @@ size_t host_mirror(fra_ctx *ctx, int slot)
         if (v >= 1) hw = (size_t)v;
     }
     const size_t n_thr = std::min<size_t>(std::min<size_t>(hw, 32), std::max<size_t>(1, total * (size_t)n >> 20));
-    if (n_thr <= 1) { work(0, total); return total; }
+    std::atomic<int> ready{0};                                         // slices whose copies have landed
+    // worker t of n_thr: its part of every slice, in slice order
+    auto work = [&](size_t t) {
+        for (int s = 0; s < plan.n_slices; ++s) {
+            const size_t nh = plan.nh[s];
+            const size_t i0 = nh * t / n_thr, i1 = nh * (t + 1) / n_thr;
+            if (i0 >= i1) continue;
+            while (ready.load(std::memory_order_acquire) <= s) std::this_thread::yield();
+            for (size_t i = i0; i < i1; ++i) {
+                const size_t f = (size_t)s * plan.per + i;
+                uint32_t *fr = reinterpret_cast<uint32_t *>(base + f * (size_t)n * 4);
+#ifdef FRA_HAVE_AVX2_PATH
+                if (avx2) { mirror_frame_avx2(fr, bits + f * words, n); continue; }
+#endif
+                mirror_frame_scalar(fr, bits + f * words, n, 1, n / 2);
+            }
+        }
+#ifdef FRA_HAVE_AVX2_PATH
+        _mm_sfence();                                                   // the non-temporal stores are visible before the join
+#endif
+    };
     std::vector<std::thread> pool;
-    const size_t per = (total + n_thr - 1) / n_thr;
-    for (size_t t = 0; t < n_thr; ++t) {
-        const size_t i0 = t * per, i1 = std::min(total, i0 + per);
-        if (i0 < i1) pool.emplace_back(work, i0, i1);
+    if (n_thr > 1)
+        for (size_t t = 0; t < n_thr; ++t) pool.emplace_back(work, t);
+    double waited = 0.0;
+    for (int s = 0; s < plan.n_slices; ++s) {
+        const auto t0 = clk::now();
+        if (cudaEvent_t e = ctx->slice_done[slot][s]) (void)cudaEventSynchronize(e);   // errors surface at the call-level events
+        waited += std::chrono::duration<double>(clk::now() - t0).count();
+        ready.store(s + 1, std::memory_order_release);
     }
+    if (n_thr == 1) work(0);                                            // small calls: no threads
     for (auto &th : pool) th.join();
+    if (wait_s) *wait_s = waited;
     return total;
 }
 
@@ -713,15 +726,16 @@ int finish_host_slot(fra_ctx *ctx, int slot)
     using clk = std::chrono::steady_clock;
     const bool pending = ctx->mirror_plan[slot].frames != nullptr;
     const auto t0 = clk::now();
+    double slice_wait = 0.0;
+    const size_t mirrored = host_mirror(ctx, slot, &slice_wait);       // slice by slice, as the copies land
+    const auto t1 = clk::now();
     for (cudaEvent_t e : ctx->host_done[slot])
         if (e) FRA_TRY(ctx, cudaEventSynchronize(e));
-    const auto t1 = clk::now();
-    const size_t mirrored = host_mirror(ctx, slot);
     const auto t2 = clk::now();
     // Balance the link against the mirror (steady state of a two-calls-in-flight loop): waiting for the copies
     // means the link is the longer side -> more half spectra; no wait at all means the mirror is -> fewer.
-    const double wait = std::chrono::duration<double>(t1 - t0).count();
-    const double mir = std::chrono::duration<double>(t2 - t1).count();
+    const double wait = slice_wait + std::chrono::duration<double>(t2 - t1).count();
+    const double mir = std::chrono::duration<double>(t1 - t0).count() - slice_wait;
     if (pending) {
         ctx->last_wait_s = wait;
         ctx->last_mirror_s = mir;
@@ -912,6 +926,9 @@ int fra_destroy(fra_ctx *ctx)
         if (ps) { cudaStreamSynchronize(ps); cudaStreamDestroy(ps); }
     for (cudaEvent_t pe : {ctx->pipe_in, ctx->pipe_go, ctx->pipe_k1_done[0], ctx->pipe_k1_done[1], ctx->pipe_k2_done[0], ctx->pipe_k2_done[1]})
         if (pe) cudaEventDestroy(pe);
+    for (auto &slot_events : ctx->slice_done)
+        for (cudaEvent_t se : slot_events)
+            if (se) cudaEventDestroy(se);
     for (auto hb : ctx->h_mbits)
         if (hb) cudaFreeHost(hb);
     void *bufs[] = {ctx->d_rom32, ctx->d_rom2x, ctx->d_twfx, ctx->d_mbits, ctx->d_skew_in, ctx->d_skew_prev, ctx->d_state, ctx->d_scratch, ctx->d_tw1, ctx->d_tw2, ctx->d_twn, ctx->d_in, ctx->d_twc, ctx->d_halves, ctx->d_split,
@@ -1276,6 +1293,11 @@ int fra_process_host_async(fra_ctx *ctx, const int16_t *h_in, int continuous, in
         } else if (h_out->d_frames) {
             FRA_TRY(ctx, cudaMemcpyAsync(h_out->d_frames + c0 * n * 4, o.d_frames, nch * n * 4, cudaMemcpyDeviceToHost, st));
             d2h += nch * n * 4;
+        }
+        if (half) {
+            cudaEvent_t &se = ctx->slice_done[id & 1][s];
+            if (!se) FRA_TRY(ctx, cudaEventCreateWithFlags(&se, cudaEventDisableTiming));
+            FRA_TRY(ctx, cudaEventRecord(se, st));
         }
         if (h_out->d_iq) {
             FRA_TRY(ctx, cudaMemcpyAsync(h_out->d_iq + c0 * n * 2, o.d_iq, nch * n * 8, cudaMemcpyDeviceToHost, st));
