@@ -504,19 +504,24 @@ FRA_DEV void fft_last_pass(const K2Args &a, const float2 *buf, int tid, int fram
         constexpr int TRIPS = SLOTS / STEP;
         static_assert(SLOTS % STEP == 0 && STEP % 128 == 0, "last pass: whole trips, swizzle-preserving stride");
         const int slot0 = tid + (CLUSTER ? rank * P::THREADS : 0);
+        // (with the optional outputs an item is several times longer and full of run-time branches: unrolling it only
+        // costs instruction-cache space - the complex64 FFT-only sweep lost 8 % at 16K - so that variant stays rolled)
+        constexpr int UNROLL = (OUT == 0) ? TRIPS : 1;
         if constexpr (STEP <= HALF) {
             // one frame per CTA (FPC = 1 whenever L = 4096 ... or two frames of 8K): k advances, the frame is fixed per trip
             static_assert(HALF % STEP == 0, "last pass: trips per frame");
             const int k0 = slot0 % HALF;
             const int sk0 = swz(k0), skm0 = swz(P::L - k0);           // (k0 = 0: L itself, so that L - ii follows from it)
-#pragma unroll
+            float2 wn_next = __ldg(a.twn + k0);                          // the next item's twiddle, one item ahead
+#pragma unroll UNROLL
             for (int i = 0; i < TRIPS; ++i) {
                 const int fr = (i * STEP) / HALF;
-                const int ii = (i * STEP) % HALF;                        // compile-time offset of k within the frame
+                const int ii = (i * STEP) % HALF;                        // (unrolled: compile-time) offset of k within the frame
                 const int k = k0 + ii;
+                const float2 wn = wn_next;
+                if (i + 1 < TRIPS) wn_next = __ldg(a.twn + k0 + ((i + 1) * STEP) % HALF);
                 const bool live = (P::FPC == 1) || (frame0 + fr < a.batch);
-                if ((ii > 0 || k0 != 0) && live)
-                    item(TagMain(), fr, k, __ldg(a.twn + k), sk0 + ii, skm0 - ii);
+                if ((ii > 0 || k0 != 0) && live) item(TagMain(), fr, k, wn, sk0 + ii, skm0 - ii);
             }
         } else {
             // several frames per trip (L = 256): k is fixed per thread, the frame advances
@@ -524,7 +529,7 @@ FRA_DEV void fft_last_pass(const K2Args &a, const float2 *buf, int tid, int fram
             const int k = slot0 % HALF;
             const int sk = swz(k), skm = swz((P::L - k) & (P::L - 1));
             const float2 wn = __ldg(a.twn + k);
-#pragma unroll
+#pragma unroll UNROLL
             for (int i = 0; i < TRIPS; ++i) {
                 const int fr = slot0 / HALF + i * (STEP / HALF);
                 if (k != 0 && frame0 + fr < a.batch) item(TagMain(), fr, k, wn, sk, skm);
