@@ -36,6 +36,9 @@ namespace fra {
 #endif
 // (Capping the kernel at 112 registers - so that one of its CTAs fits beside three CTAs of the lane-per-channel
 // window+IIR kernel in pipelined mode - compiles without spills and changes nothing: 2.93 ms per step either way.)
+#ifndef FRA_K2_EARLY_BARRIER
+#define FRA_K2_EARLY_BARRIER 1
+#endif
 #ifndef FRA_K2_MINBLOCKS
 #define FRA_K2_MINBLOCKS 2
 #endif
@@ -302,13 +305,13 @@ FRA_DEV void fft_pass(const K2Args &a, float2 *buf, int tid, int frame0, const u
         }
     }
     // butterfly q of this thread: inputs (+ twiddles) -> 16-point DFT in o; wbase / jlow describe where it goes
-    auto compute = [&](int q, float2 (&o)[16], int &wbase, int &jlow) {
+    // inputs (+ twiddles) of butterfly q of this thread -> v; wbase / jlow describe where its outputs go
+    auto gather = [&](int q, float2 (&v)[16], int &wbase, int &jlow) {
         const int it = tid + P::THREADS * q;
         const int j = it % P::NB;
         const int f = (it / P::NB) % P::FLOC;               // sub-sequence within this CTA's buffer
         const int fr = it / (P::NB * P::FLOC);
         const int base = fr * P::MLOC + f * P::L;
-        float2 v[16];
         if (PASS == 0) {
             const int frame = frame0 + fr;
             const bool live = frame < a.batch;
@@ -348,6 +351,10 @@ FRA_DEV void fft_pass(const K2Args &a, float2 *buf, int tid, int frame0, const u
             wbase = base + (j / ns) * ns * 16 + k;     // out[.. + r ns]
             jlow = k;
         }
+    };
+    auto compute = [&](int q, float2 (&o)[16], int &wbase, int &jlow) {
+        float2 v[16];
+        gather(q, v, wbase, jlow);
         dft16(v, o);
     };
     auto store = [&](const float2 (&o)[16], int wbase, int jlow) {
@@ -368,7 +375,23 @@ FRA_DEV void fft_pass(const K2Args &a, float2 *buf, int tid, int frame0, const u
             for (int r = 0; r < 16; ++r) p[256 * r] = o[r];
         }
     };
-    if (HAZARD || FRA_K2_SEQ == 0) {
+    if (HAZARD && FRA_K2_EARLY_BARRIER) {
+        // the barrier sits between the reads and the butterflies (not between the butterflies and the writes): every
+        // thread has its inputs in registers, and the scattered 8-byte stores then leave one butterfly at a time,
+        // interleaved with the other one's arithmetic, instead of 32 per thread in one burst behind the barrier
+        // (that burst was 7.6 % of the kernel's warp samples, 59 % of them mio_throttle)
+        float2 v[IPT][16];
+        int wbase[IPT], jlow[IPT];
+#pragma unroll
+        for (int q = 0; q < IPT; ++q) gather(q, v[q], wbase[q], jlow[q]);
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < IPT; ++q) {
+            float2 o[16];
+            dft16(v[q], o);
+            store(o, wbase[q], jlow[q]);
+        }
+    } else if (HAZARD || FRA_K2_SEQ == 0) {
         float2 o[IPT][16];
         int wbase[IPT], jlow[IPT];
 #pragma unroll
