@@ -330,7 +330,8 @@ def run_ours(args):
     # The e2e context may send frames as bins 0..N/2 + one bit per bin and complete the Hermitian half on the host
     # (FRA_HOST_HALF_SPECTRUM: byte-identical frames, 2.06 instead of 4 B per sample device-to-host).  The library
     # completes the upper halves slice by slice while the later slices still cross the link, and can send a share
-    # of the frames whole (adapted from the wait / mirror split; it stays at 1 on the hosts measured).  Used when at
+    # of the frames whole (found by a short search over the first calls: link-bound hosts end at 1, memory-bound
+    # ones near 5/8).  Used when at
     # most two ranks share the host: the mirror costs host memory bandwidth (8 instead of 6 B per sample), and with
     # eight ranks on one host that is the bottleneck, not the links (tools/e2e_probe_multi.sh, profiles/r02_e2e_*:
     # full frames 34, adaptive 25, all-half 19 Gsamples/s over eight GPUs).  FRA_BENCH_HALF=0/1 overrides.
@@ -372,7 +373,7 @@ def run_ours(args):
         _ = int(pending[0]["frames"][0, 0])
         return moved
 
-    host_loop(14 if use_half else 3, True)                  # warm-up: pinned output sets allocated, the share settles
+    host_loop(18 if use_half else 3, True)                  # warm-up: pinned output sets allocated, the share search (<= 17 calls) ends
     barrier(seq)
     e2e_steps = max(3, min(args.steps, 10))
     t0 = time.perf_counter()

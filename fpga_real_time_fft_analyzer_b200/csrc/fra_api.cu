@@ -122,12 +122,22 @@ struct fra_ctx {
         size_t per = 0, nh[8] = {0};
         int n_slices = 0;
     } mirror_plan[2];
-    // share of the frames that travel as half spectra: the rest go whole, so that the link (DMA) and the host's
-    // cores (mirror) finish together.  Adapted per call from the time fra_host_wait spent waiting for the copies
-    // against the time it spent mirroring; half_step halves at every reversal.
-    double half_frac = 1.0, half_step = 0.125;
-    int half_dir = 0;
+    // Share of the frames that travel as half spectra; the rest go whole.  More half spectra = less device-to-host
+    // link traffic (2.06 instead of 4 B per sample) but more host memory traffic (the mirror reads and writes what the
+    // DMA would only have written: 8.06 instead of 6 B per sample in total), and which of the two binds depends on the
+    // host.  Adaptive mode measures it: a short search over the cadence of the caller's fra_process_host_async calls -
+    // three calls per trial share, the interval before the next trial's first call is the trial's step time
+    // (1, 3/4, 1/2, then the two neighbours of the best at 1/8) - and then keeps the best share.
+    double half_frac = 1.0;
     bool half_adaptive = true;
+    struct HalfTuner {
+        int calls = 0;                     // half-spectrum calls seen since the search started
+        double trial_share[5] = {1.0, 0.75, 0.5, 0.0, 0.0};
+        double trial_time[5] = {0, 0, 0, 0, 0};
+        int n_trials = 3;
+        bool done = false;
+        std::chrono::steady_clock::time_point last_entry;
+    } tuner;
     uint64_t last_h2d_bytes = 0, last_d2h_bytes = 0;
     cudaEvent_t slice_done[2][8] = {{nullptr}};      // per call slot and channel slice: its device-to-host copies
     double last_wait_s = 0.0, last_mirror_s = 0.0;   // of the newest finished call: blocked on its copies / mirroring
@@ -727,28 +737,17 @@ int finish_host_slot(fra_ctx *ctx, int slot)
     const bool pending = ctx->mirror_plan[slot].frames != nullptr;
     const auto t0 = clk::now();
     double slice_wait = 0.0;
-    const size_t mirrored = host_mirror(ctx, slot, &slice_wait);       // slice by slice, as the copies land
+    (void)host_mirror(ctx, slot, &slice_wait);                         // slice by slice, as the copies land
     const auto t1 = clk::now();
     for (cudaEvent_t e : ctx->host_done[slot])
         if (e) FRA_TRY(ctx, cudaEventSynchronize(e));
     const auto t2 = clk::now();
-    // Balance the link against the mirror (steady state of a two-calls-in-flight loop): waiting for the copies
-    // means the link is the longer side -> more half spectra; no wait at all means the mirror is -> fewer.
+    // (reported by fra_get_host_transfer: how long this thread was blocked on copies, how long the mirror ran on)
     const double wait = slice_wait + std::chrono::duration<double>(t2 - t1).count();
     const double mir = std::chrono::duration<double>(t1 - t0).count() - slice_wait;
     if (pending) {
         ctx->last_wait_s = wait;
         ctx->last_mirror_s = mir;
-    }
-    if (pending && ctx->half_adaptive && ctx->host_calls >= 3) {
-        int dir = 0;
-        if (wait > 0.10 * (wait + mir)) dir = +1;
-        else if (wait < 0.02 * (wait + mir) && mirrored > 0) dir = -1;
-        if (dir != 0) {
-            if (ctx->half_dir != 0 && dir != ctx->half_dir) ctx->half_step = std::max(1.0 / 64.0, ctx->half_step * 0.5);
-            ctx->half_dir = dir;
-            ctx->half_frac = std::min(1.0, std::max(0.0, ctx->half_frac + dir * ctx->half_step));
-        }
     }
     return FRA_OK;
 }
@@ -1010,8 +1009,7 @@ int fra_set_host_half_share(fra_ctx *ctx, double share)
     if (!ctx || share > 1.0) return FRA_ERR_INVALID;
     ctx->half_adaptive = share < 0.0;
     ctx->half_frac = share < 0.0 ? 1.0 : share;
-    ctx->half_step = 0.125;
-    ctx->half_dir = 0;
+    ctx->tuner = fra_ctx::HalfTuner();
     return FRA_OK;
 }
 
@@ -1250,6 +1248,35 @@ int fra_process_host_async(fra_ctx *ctx, const int16_t *h_in, int continuous, in
     plan.frames = h_out->d_frames;
     plan.per = per;
     plan.n_slices = n_slices;
+    if (half && ctx->half_adaptive && !ctx->tuner.done) {
+        // the search (see HalfTuner): trial i covers calls 3 i + 1 .. 3 i + 3 (call 0 is warm-up: allocations)
+        auto &tu = ctx->tuner;
+        const auto now = std::chrono::steady_clock::now();
+        const int k = tu.calls - 1;                                   // calls of the search proper made so far
+        if (k >= 3 && k % 3 == 0) {                                   // first call after a trial: the trial's step time
+            tu.trial_time[k / 3 - 1] = std::chrono::duration<double>(now - tu.last_entry).count();
+            if (k / 3 == 3) {
+                // coarse result: refine around the best of 1, 3/4, 1/2
+                int b = 0;
+                for (int i = 1; i < 3; ++i)
+                    if (tu.trial_time[i] < tu.trial_time[b]) b = i;
+                const double c = tu.trial_share[b];
+                tu.n_trials = 3;
+                if (c + 0.125 <= 1.0) tu.trial_share[tu.n_trials++] = c + 0.125;
+                tu.trial_share[tu.n_trials++] = c - 0.125;
+            }
+            if (k / 3 == tu.n_trials) {
+                int b = 0;
+                for (int i = 1; i < tu.n_trials; ++i)
+                    if (tu.trial_time[i] < tu.trial_time[b]) b = i;
+                ctx->half_frac = tu.trial_share[b];
+                tu.done = true;
+            }
+        }
+        if (!tu.done && k >= 0) ctx->half_frac = tu.trial_share[std::min(k / 3, tu.n_trials - 1)];
+        tu.last_entry = now;
+        tu.calls++;
+    }
     const double half_frac = ctx->half_frac;
     uint64_t d2h = 0;
     for (int s = 0; s < n_slices && rc == FRA_OK; ++s) {

@@ -195,13 +195,14 @@ int fra_process_host_async(fra_ctx *ctx, const int16_t *h_in, int continuous, in
 int fra_host_wait(fra_ctx *ctx, uint64_t ticket);
 
 /* FRA_HOST_HALF_SPECTRUM contexts: the share of a call's frames that cross the link as half spectra (the rest go
- * whole, so that the DMA engines and the host cores that complete the mirror finish together).  share in [0, 1]
- * fixes it; a negative value (the default) lets fra_host_wait adapt it from call to call: time spent waiting for
- * the copies means the link is the longer side (more half spectra), no wait means the mirror is (fewer).
- * fra_get_host_transfer reports the bytes the last fra_process_host[_async] call moved each way, the share the
- * next call will use, and for the newest half-spectrum call that fra_host_wait finished how long it was blocked on
- * the copies and how long the mirror took (seconds; any pointer may be NULL).  The frames are byte-identical
- * whatever the share. */
+ * whole).  Half spectra halve the device-to-host link traffic but cost host memory traffic (the mirror reads and
+ * writes what the DMA would only have written); which of the two binds depends on the host.  share in [0, 1] fixes
+ * it; a negative value (the default) lets the library measure: over the first 14-17 calls it tries 1, 3/4, 1/2 and
+ * the neighbours of the best (three calls each, timing the cadence of the caller's fra_process_host_async calls) and
+ * then keeps the fastest.  fra_get_host_transfer reports the bytes the last fra_process_host[_async] call moved each
+ * way, the share the next call will use, and for the newest half-spectrum call that fra_host_wait finished how long
+ * it was blocked on the copies and how long the mirror ran on after them (seconds; any pointer may be NULL).  The
+ * frames are byte-identical whatever the share. */
 int fra_set_host_half_share(fra_ctx *ctx, double share);
 int fra_get_host_transfer(const fra_ctx *ctx, uint64_t *h2d_bytes, uint64_t *d2h_bytes, double *half_share, double *wait_s,
                           double *mirror_s);

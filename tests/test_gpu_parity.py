@@ -621,7 +621,7 @@ def test_half_spectrum_host_transfer(fra, rom, n, c):
         half.set_host_half_share(-1.0)
         ref0 = full.process_host(xs[2], continuous=False, want=("frames",))["frames"].clone()
         pending = None
-        for i in range(8):
+        for i in range(19):                             # the share search takes at most 17 calls
             cur = half.process_host_async(xs[2], continuous=False, want=("frames",))
             if pending is not None:
                 half.host_wait(pending[1])
@@ -629,4 +629,4 @@ def test_half_spectrum_host_transfer(fra, rom, n, c):
             pending = cur
         half.host_wait(pending[1])
         assert torch.equal(pending[0]["frames"], ref0)
-        assert 0.0 <= half.host_transfer()[2] <= 1.0
+        assert half.host_transfer()[2] in (1.0, 0.875, 0.75, 0.625, 0.5, 0.375)
