@@ -698,7 +698,11 @@ constexpr int kDuoSmemBytes = kDuoRomOff + 2 * kDuoRomBytes;                // 7
 // one CTA of this kernel and two of the FFT fit an SM (97 + 65 + 65 KiB), but TWO of this
 // kernel beside an FFT CTA do not, so its 128 CTAs cannot double up on SMs the FFT already
 // occupies (measured: 0.273 -> 0.260 ms per step in the pipeline's good mode).
+#ifdef FRA_DUO_SMEM_REQUEST
+constexpr int kDuoSmemRequest = FRA_DUO_SMEM_REQUEST;
+#else
 constexpr int kDuoSmemRequest = 96 * 1024;
+#endif
 
 
 // Every stage warp runs the SAME branch-free straight-line chunk body: the last pair also
@@ -890,8 +894,13 @@ FRA_DEV void duo_store_state(const K1Args &a, int c, int s, const StageState &st
 // ALT: the six stages use two alternating coefficient sets (the RTL's bank layout): the pair's
 // coefficients are then compile-time addresses and stay in uniform registers (a run-time set index
 // moves them to vector registers and costs 5 %)
+#ifdef FRA_DUO_MAXNREG
+#define FRA_DUO_BOUNDS __maxnreg__(FRA_DUO_MAXNREG)
+#else
+#define FRA_DUO_BOUNDS __launch_bounds__(kDuoWarps * 32, 2)
+#endif
 template <bool B1Z, int FAST, bool ALT>
-__global__ void __launch_bounds__(kDuoWarps * 32, 2) k1_duo(K1Args a)
+__global__ void FRA_DUO_BOUNDS k1_duo(K1Args a)
 {
     FRA_DYN_SMEM(smem_raw);
     float *smem = reinterpret_cast<float *>(smem_raw);
