@@ -39,6 +39,7 @@ FRA_FFT_FIXED16 = 0x200
 FRA_K2_64K_SPLIT = 0x400
 FRA_HOST_HALF_SPECTRUM = 0x800
 FRA_WINDOW_RTL_SKEW = 0x1000
+FRA_K2_WIDE_CTA = 0x2000
 
 
 class FraOutputs(C.Structure):

@@ -288,32 +288,33 @@ int launch_k2_n(fra_ctx *ctx, const K2Args &args, bool win, int qmode, cudaStrea
 }
 
 #ifndef FRA_HOST_EMUL
-// N = 65536 on chip: one frame per cluster of two CTAs (k2_fft.cuh: k2_fft64k_cluster)
-template <bool WIN, int QMODE>
-int launch_k2_64k_cluster_inst(fra_ctx *ctx, K2Args args, cudaStream_t st)
+// N = 32768 / 65536 on chip: one frame per cluster of R CTAs (k2_fft.cuh: k2_fft_cluster)
+template <int LOG2N, int R, bool WIN, int QMODE>
+int launch_k2_cluster_inst(fra_ctx *ctx, K2Args args, cudaStream_t st)
 {
-    using P = FftPlan64kCluster;
+    using P = FftPlanCluster<LOG2N, R>;
     const bool frames_only = args.frames && !args.iq && !args.mag && !args.phase;
-    auto kfn = frames_only ? k2_fft64k_cluster<WIN, QMODE, 0> : k2_fft64k_cluster<WIN, QMODE, 1>;
+    auto kfn = frames_only ? k2_fft_cluster<LOG2N, R, WIN, QMODE, 0> : k2_fft_cluster<LOG2N, R, WIN, QMODE, 1>;
     FRA_SMEM(ctx, kfn, P::SMEM_BYTES);
-    args.twn = ctx->d_twc;                                   // W_65536^e
+    if (LOG2N == 16) args.twn = ctx->d_twc;                  // W_65536^e
     if (args.batch <= 0) return FRA_OK;
-    kfn<<<dim3(2 * (unsigned)args.batch), dim3(P::THREADS), (size_t)P::SMEM_BYTES, st>>>(args);    // __cluster_dims__(2, 1, 1)
+    kfn<<<dim3((unsigned)R * (unsigned)args.batch), dim3(P::THREADS), (size_t)P::SMEM_BYTES, st>>>(args);    // __cluster_dims__(R, 1, 1)
     FRA_TRY(ctx, cudaGetLastError());
     ctx->last_kernels++;
     return FRA_OK;
 }
 
-int launch_k2_64k_cluster(fra_ctx *ctx, const K2Args &args, bool win, int qmode, cudaStream_t st)
+template <int LOG2N, int R>
+int launch_k2_cluster(fra_ctx *ctx, const K2Args &args, bool win, int qmode, cudaStream_t st)
 {
     if (win) {
-        if (qmode == 0) return launch_k2_64k_cluster_inst<true, 0>(ctx, args, st);
-        if (qmode == 1) return launch_k2_64k_cluster_inst<true, 1>(ctx, args, st);
-        return launch_k2_64k_cluster_inst<true, 2>(ctx, args, st);
+        if (qmode == 0) return launch_k2_cluster_inst<LOG2N, R, true, 0>(ctx, args, st);
+        if (qmode == 1) return launch_k2_cluster_inst<LOG2N, R, true, 1>(ctx, args, st);
+        return launch_k2_cluster_inst<LOG2N, R, true, 2>(ctx, args, st);
     }
-    if (qmode == 0) return launch_k2_64k_cluster_inst<false, 0>(ctx, args, st);
-    if (qmode == 1) return launch_k2_64k_cluster_inst<false, 1>(ctx, args, st);
-    return launch_k2_64k_cluster_inst<false, 2>(ctx, args, st);
+    if (qmode == 0) return launch_k2_cluster_inst<LOG2N, R, false, 0>(ctx, args, st);
+    if (qmode == 1) return launch_k2_cluster_inst<LOG2N, R, false, 1>(ctx, args, st);
+    return launch_k2_cluster_inst<LOG2N, R, false, 2>(ctx, args, st);
 }
 #endif
 
@@ -322,7 +323,9 @@ int launch_k2_64k_cluster(fra_ctx *ctx, const K2Args &args, bool win, int qmode,
 int launch_k2_64k(fra_ctx *ctx, const K2Args &args, bool win, int qmode, cudaStream_t st)
 {
 #ifndef FRA_HOST_EMUL
-    if (!(ctx->flags & FRA_K2_64K_SPLIT)) return launch_k2_64k_cluster(ctx, args, win, qmode, st);
+    if (!(ctx->flags & FRA_K2_64K_SPLIT))
+        return (ctx->flags & FRA_K2_WIDE_CTA) ? launch_k2_cluster<16, 2>(ctx, args, win, qmode, st)
+                                              : launch_k2_cluster<16, 4>(ctx, args, win, qmode, st);
 #endif
     // scratch is indexed by the frame's position in the context, so channel slices on different
     // streams (fra_process_host) do not share it
@@ -418,7 +421,11 @@ int launch_k2(fra_ctx *ctx, const K2Args &args, bool win, int qmode, cudaStream_
     case 12: return launch_k2_n<12>(ctx, args, win, qmode, st);
     case 13: return launch_k2_n<13>(ctx, args, win, qmode, st);
     case 14: return launch_k2_n<14>(ctx, args, win, qmode, st);
-    case 15: return launch_k2_n<15>(ctx, args, win, qmode, st);
+    case 15:
+#ifndef FRA_HOST_EMUL
+        if (!(ctx->flags & FRA_K2_WIDE_CTA)) return launch_k2_cluster<15, 2>(ctx, args, win, qmode, st);
+#endif
+        return launch_k2_n<15>(ctx, args, win, qmode, st);
     case 16: return launch_k2_64k(ctx, args, win, qmode, st);
     default: return FRA_ERR_UNSUPPORTED;
     }

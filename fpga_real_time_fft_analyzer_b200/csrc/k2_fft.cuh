@@ -81,23 +81,33 @@ struct FftPlan {
     static constexpr int MLOC = M;                              // complex points per frame in one CTA's buffer
 };
 
-// N = 65536 on chip: 32768 complex points are 256 KiB of fp32 - two CTAs of a thread-block cluster hold four
-// of the eight length-4096 sub-sequences each (128 KiB), run their sub-FFTs locally, and the last pass reads
-// the partner's half through distributed shared memory (k2_fft64k_cluster below).
-struct FftPlan64kCluster {
-    static constexpr int N = 65536;
+// N = 32768 / 65536 across a thread-block cluster: the F = M / 4096 sub-sequences of a frame are divided over the R
+// CTAs of a cluster (FLOC = F / R each), every CTA runs its sub-FFTs locally, and the last pass reads the other
+// CTAs' sub-sequences through distributed shared memory (k2_fft_cluster below).
+//   <16, 2>: 65536 points as two CTAs of 128 KiB / 512 threads (32768 complex points are 256 KiB of fp32, more than
+//            one SM has): one CTA per SM
+//   <16, 4>: the same frame as four CTAs of 64 KiB / 256 threads: two CTAs per SM, so one CTA's passes run beside
+//            the other's loads, barriers and stores (what the 16K kernel gains from two CTAs per SM)
+//   <15, 2>: 32768 points as two CTAs of 64 KiB / 256 threads instead of one CTA of 128 KiB / 512 threads
+template <int LOG2N, int R>
+struct FftPlanCluster {
+    static constexpr int N = 1 << LOG2N;
     static constexpr int M = N / 2;
     static constexpr int L = 4096;
-    static constexpr int F = 8;
+    static constexpr int F = M / L;
     static constexpr int NB = L / 16;
     static constexpr int PASSES = 3;
     static constexpr int FPC = 1;
-    static constexpr int FLOC = 4;
+    static constexpr int RANKS = R;
+    static constexpr int FLOC = F / R;
     static constexpr int MLOC = FLOC * L;
     static constexpr int ITEMS = FLOC * NB;
-    static constexpr int THREADS = ITEMS / 2;                   // 512
-    static constexpr int SMEM_BYTES = MLOC * 8;                 // 128 KiB per CTA
+    static constexpr int THREADS = ITEMS / 2;                   // 512 (FLOC = 4) or 256 (FLOC = 2)
+    static constexpr int SMEM_BYTES = MLOC * 8;                 // 128 or 64 KiB per CTA
+    static constexpr int MINBLOCKS = (SMEM_BYTES <= 64 * 1024) ? 2 : 1;
+    static_assert(F % R == 0 && FLOC >= 1, "cluster plan: whole sub-sequences per CTA");
 };
+using FftPlan64kCluster = FftPlanCluster<16, 2>;
 
 // two packed int16 -> two floats: one I2F.S16 each, reading the register's low / high half
 // directly (conversion unit; two issue slots per pair instead of the five of an ALU/FMA-pipe
@@ -285,7 +295,8 @@ FRA_DEV void fft_pass(const K2Args &a, float2 *buf, int tid, int frame0, const u
     constexpr int IPT = P::ITEMS / P::THREADS;          // butterflies per thread per pass (2)
     // N = 16384: THREADS = NB and F = 2, so a thread's two butterflies are column j = tid of the
     // sub-sequences f = 0 and f = 1, whose input words are adjacent: one 64-bit load for both
-    constexpr bool PAIRED = FRA_K2_PAIRED && (PASS == 0) && (P::F == 2) && (P::THREADS == P::NB) && (IPT == 2) && (P::FPC == 1);
+    // (in a cluster with two sub-sequences per CTA, f0 and f0 + 1, the same holds with a stride of F words)
+    constexpr bool PAIRED = FRA_K2_PAIRED && (PASS == 0) && (P::FLOC == 2) && (P::THREADS == P::NB) && (IPT == 2) && (P::FPC == 1);
     // the middle pass of L = 4096 scatters into other threads' read positions: all reads, a barrier, all
     // writes (both butterflies' outputs live across it).  Every other pass writes where nobody else reads
     // in that pass (pass 0 reads global memory; the last pass of each size writes back to the positions
@@ -299,9 +310,9 @@ FRA_DEV void fft_pass(const K2Args &a, float2 *buf, int tid, int frame0, const u
             for (int r = 0; r < 16; ++r) pre[r] = staged[tid + P::NB * r];
         } else {
             const bool live = frame0 < a.batch;
-            const uint2 *src = reinterpret_cast<const uint2 *>(a.in + (size_t)frame0 * P::M) + tid;
+            const uint2 *src = reinterpret_cast<const uint2 *>(a.in + (size_t)frame0 * P::M + f0) + (P::F / 2) * tid;
 #pragma unroll
-            for (int r = 0; r < 16; ++r) pre[r] = live ? __ldg(src + P::NB * r) : make_uint2(0u, 0u);   // z[2 (j + NB r) + {0, 1}]
+            for (int r = 0; r < 16; ++r) pre[r] = live ? __ldg(src + (P::F / 2) * P::NB * r) : make_uint2(0u, 0u);   // z[F (j + NB r) + f0 + {0, 1}]
         }
     }
     // butterfly q of this thread: inputs (+ twiddles) -> 16-point DFT in o; wbase / jlow describe where it goes
@@ -419,6 +430,36 @@ FRA_DEV void fft_pass(const K2Args &a, float2 *buf, int tid, int frame0, const u
     __syncthreads();
 }
 
+// ---------------------------------------------------- thread-block cluster helpers (N = 32768 / 65536 kernels below)
+#ifndef FRA_HOST_EMUL
+FRA_DEV unsigned cluster_ctarank()
+{
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+FRA_DEV void cluster_barrier()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// the partner CTA's copy of a shared-memory address of this CTA, as a generic pointer (DSMEM window)
+FRA_DEV const float2 *cluster_map(const float2 *p, unsigned rank)
+{
+    unsigned long long out;
+    asm volatile("mapa.u64 %0, %1, %2;" : "=l"(out) : "l"((unsigned long long)(uintptr_t)p), "r"(rank));
+    return reinterpret_cast<const float2 *>((uintptr_t)out);
+}
+
+#endif
+template <class P, bool CLUSTER>
+struct ClusterRanks {
+    static constexpr int value = 1;
+};
+template <class P>
+struct ClusterRanks<P, true> {
+    static constexpr int value = P::RANKS;
+};
+
 template <bool B>
 struct BoolTag {
     static constexpr bool value = B;
@@ -427,11 +468,22 @@ struct BoolTag {
 // OUT = 0: int16 frames only (the hot configuration); OUT = 1: any combination of
 // outputs, selected at run time by the null pointers in K2Args.
 // the last pass of the CTA's frames [frame0, frame0 + FPC): radix-F combine, untangle, mirror, pack.
-// CLUSTER (FftPlan64kCluster): the eight sub-sequences live in two CTAs' buffers - f / 4 == rank in `buf`, the
-// others in `remote` (the partner's buffer through distributed shared memory) - and each CTA does half of the items.
+// CLUSTER (FftPlanCluster): the F sub-sequences live in the buffers of the cluster's RANKS CTAs - f / FLOC == rank in
+// `buf`, the others in the buffer of CTA f / FLOC (`buf` mapped into that CTA's distributed-shared-memory window) -
+// and each CTA does 1 / RANKS of the items.
 template <class P, int QMODE, int OUT, bool CLUSTER = false>
-FRA_DEV void fft_last_pass(const K2Args &a, const float2 *buf, int tid, int frame0, const float2 *remote = nullptr, int rank = 0)
+FRA_DEV void fft_last_pass(const K2Args &a, const float2 *buf, int tid, int frame0, int rank = 0)
 {
+    constexpr int RANKS = ClusterRanks<P, CLUSTER>::value;
+    const float2 *peer[RANKS];
+#pragma unroll
+    for (int r = 0; r < RANKS; ++r) peer[r] = buf;
+#if !defined(FRA_HOST_EMUL)
+    if constexpr (CLUSTER) {
+#pragma unroll
+        for (int r = 0; r < RANKS; ++r) peer[r] = (r == rank) ? buf : cluster_map(buf, (unsigned)r);
+    }
+#endif
 
     // ---------------- last pass: radix-F combine + untangle + mirror + pack
     BinOut out;
@@ -452,10 +504,20 @@ FRA_DEV void fft_last_pass(const K2Args &a, const float2 *buf, int tid, int fram
         const int km = (P::L - k) & (P::L - 1);
         const int sk = MAIN ? sk_in : swz(k), skm = MAIN ? skm_in : swz(km);   // f L is a multiple of 8 rows
         float2 za[P::F], zb[P::F];
+        // W_M^(f k) = W_N^(2 f k) from W_N^k by squaring and multiplying (f = 2 m: the square of m's, f = 2 m + 1: f - 1's
+        // times W_M^k) instead of F - 2 gathers of stride 2 f from the table: those touched up to 28 cache lines per warp
+        // load at F = 8 and put the last pass of the 32K / 64K kernels behind lg_throttle / long_scoreboard; at most five
+        // roundings deep, far inside the FFT's own rounding error
+        float2 wp[P::F > 1 ? P::F : 2];
+        wp[1] = make_float2(wn.x * wn.x - wn.y * wn.y, 2.0f * wn.x * wn.y);
+#pragma unroll
+        for (int f = 2; f < P::F; ++f)
+            wp[f] = (f & 1) ? cmul(wp[f - 1], wp[1])
+                            : make_float2(wp[f / 2].x * wp[f / 2].x - wp[f / 2].y * wp[f / 2].y, 2.0f * wp[f / 2].x * wp[f / 2].y);
 #pragma unroll
         for (int f = 0; f < P::F; ++f) {
             if (CLUSTER) {
-                const float2 *b = ((f / P::FLOC) == rank) ? buf : remote;
+                const float2 *b = peer[f / P::FLOC];
                 za[f] = b[(f % P::FLOC) * P::L + sk];
                 zb[f] = b[(f % P::FLOC) * P::L + skm];
             } else {
@@ -463,9 +525,7 @@ FRA_DEV void fft_last_pass(const K2Args &a, const float2 *buf, int tid, int fram
                 zb[f] = buf[fr * P::M + f * P::L + skm];
             }
             if (f > 0) {
-                // W_M^(f k) = W_N^(2 f k); f = 1 by squaring W_N^k, saving a load
-                const float2 w = (f == 1) ? make_float2(wn.x * wn.x - wn.y * wn.y, 2.0f * wn.x * wn.y)
-                                          : __ldg(a.twn + 2 * f * k);
+                const float2 w = wp[f];
                 za[f] = cmul(za[f], w);
                 // W_M^(f (L-k)) = W_F^f * conj(W_M^(f k))
                 float2 t = cmulc(zb[f], w);
@@ -523,7 +583,7 @@ FRA_DEV void fft_last_pass(const K2Args &a, const float2 *buf, int tid, int fram
     {
         constexpr int HALF = P::L / 2;
         constexpr int SLOTS = P::FPC * HALF;
-        constexpr int STEP = CLUSTER ? 2 * P::THREADS : P::THREADS;
+        constexpr int STEP = RANKS * P::THREADS;
         constexpr int TRIPS = SLOTS / STEP;
         static_assert(SLOTS % STEP == 0 && STEP % 128 == 0, "last pass: whole trips, swizzle-preserving stride");
         const int slot0 = tid + (CLUSTER ? rank * P::THREADS : 0);
@@ -560,7 +620,7 @@ FRA_DEV void fft_last_pass(const K2Args &a, const float2 *buf, int tid, int fram
         }
     }
     // the two self-paired items k = 0 and k = L/2 of every frame in the CTA (in a cluster: one each)
-    if (tid < 2 * P::FPC && (!CLUSTER || (tid & 1) == rank)) {
+    if (tid < 2 * P::FPC && (!CLUSTER || (tid & 1) == rank)) {        // (in a cluster: ranks 0 and 1 take one each)
         const int fr = tid >> 1;
         const int k = (tid & 1) ? (P::L / 2) : 0;
         if (frame0 + fr < a.batch) item(TagEdge(), fr, k, __ldg(a.twn + k), 0, 0);
@@ -653,49 +713,31 @@ __global__ void __launch_bounds__(FftPlan<kStagedLog2N>::THREADS, FRA_K2_MINBLOC
 #endif
 }
 
-// ---------------------------------------------------- N = 65536 on chip (cluster of two CTAs)
-// One frame per 2-CTA thread-block cluster.  CTA `rank` owns the sub-sequences f = 4 rank .. 4 rank + 3 of
-// the eight (z[8 m + f], 4096 points each): three radix-16 passes in its own 128 KiB, exactly the code of the
-// single-CTA sizes.  After a cluster barrier the last pass - radix-8 combine, untangle, mirror, pack - takes
-// half of the items in each CTA and reads the partner's four sub-sequences through distributed shared memory
-// (64 KiB per CTA and frame over the SM-to-SM network); a second cluster barrier keeps both buffers alive
-// until both CTAs are done.  One HBM round trip per frame (2 B in, 4 B out per sample) instead of the 28 B of
-// the three-kernel path below.  a.twn = W_65536^e.
+// ---------------------------------------------------- N = 32768 / 65536 on chip (thread-block cluster)
+// One frame per R-CTA thread-block cluster.  CTA `rank` owns the sub-sequences f = FLOC rank .. FLOC rank + FLOC - 1
+// of the F (z[F m + f], 4096 points each): three radix-16 passes in its own shared memory, exactly the code of
+// the single-CTA sizes.  After a cluster barrier the last pass - radix-F combine, untangle, mirror, pack - takes
+// 1 / R of the items in each CTA and reads the other CTAs' sub-sequences through distributed shared memory
+// (the SM-to-SM network); a second cluster barrier keeps all buffers alive until every CTA is done.  One HBM round
+// trip per frame (2 B in, 4 B out per sample) - for 64K frames instead of the 28 B of the three-kernel path below.
+// a.twn = W_N^e.
 #ifndef FRA_HOST_EMUL
-FRA_DEV unsigned cluster_ctarank()
+template <int LOG2N, int R, bool WIN, int QMODE, int OUT>
+__global__ void __cluster_dims__(R, 1, 1) __launch_bounds__(FftPlanCluster<LOG2N, R>::THREADS, FftPlanCluster<LOG2N, R>::MINBLOCKS)
+    k2_fft_cluster(K2Args a)
 {
-    unsigned r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-FRA_DEV void cluster_barrier()
-{
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// the partner CTA's copy of a shared-memory address of this CTA, as a generic pointer (DSMEM window)
-FRA_DEV const float2 *cluster_map(const float2 *p, unsigned rank)
-{
-    unsigned long long out;
-    asm volatile("mapa.u64 %0, %1, %2;" : "=l"(out) : "l"((unsigned long long)(uintptr_t)p), "r"(rank));
-    return reinterpret_cast<const float2 *>((uintptr_t)out);
-}
-
-template <bool WIN, int QMODE, int OUT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FftPlan64kCluster::THREADS, 1) k2_fft64k_cluster(K2Args a)
-{
-    using P = FftPlan64kCluster;
+    using P = FftPlanCluster<LOG2N, R>;
     FRA_DYN_SMEM(smem_raw);
     float2 *buf = reinterpret_cast<float2 *>(smem_raw);
     const int tid = threadIdx.x;
     const int rank = (int)cluster_ctarank();
-    const int frame = blockIdx.x >> 1;                       // both CTAs of a cluster: the same frame, never past the batch
+    const int frame = blockIdx.x / R;                        // all CTAs of a cluster: the same frame, never past the batch
     fft_pass<P, WIN, 0>(a, buf, tid, frame, nullptr, P::FLOC * rank);
     fft_pass<P, WIN, 1>(a, buf, tid, frame, nullptr, P::FLOC * rank);
     fft_pass<P, WIN, 2>(a, buf, tid, frame, nullptr, P::FLOC * rank);
-    cluster_barrier();                                       // both halves of the frame are transformed
-    const float2 *remote = cluster_map(buf, (unsigned)(rank ^ 1));
-    fft_last_pass<P, QMODE, OUT, true>(a, buf, tid, frame, remote, rank);
-    cluster_barrier();                                       // nobody leaves while the partner still reads its buffer
+    cluster_barrier();                                       // every part of the frame is transformed
+    fft_last_pass<P, QMODE, OUT, true>(a, buf, tid, frame, rank);
+    cluster_barrier();                                       // nobody leaves while another CTA still reads its buffer
 }
 #endif
 

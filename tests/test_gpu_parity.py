@@ -483,6 +483,38 @@ def test_64k_frames_full_chain(fra, rom):
         assert np.array_equal(host["frames"].numpy(), out["frames"])
 
 
+@pytest.mark.parametrize("n", [32768, 65536])
+def test_cluster_and_wide_cta_frames_agree(fra, rom, n):
+    """32K / 64K frames: the default (64 KiB CTAs in a cluster of two / four, sub-sequences exchanged through
+    distributed shared memory) against FRA_K2_WIDE_CTA (128 KiB CTAs: 32K in one CTA, 64K in a cluster of two).
+    Both within tolerance of float64 and of each other, frames equal up to the last bit of a few bins."""
+    rng = np.random.default_rng(n + 7)
+    c = 7
+    x = adversarial(rng, c, n)
+    outs = []
+    for flags in (0, fra._abi.FRA_K2_WIDE_CTA):
+        with fra.FraContext(c, n, flags=flags) as ctx:
+            spec = ctx.fft_only(dev(x)).cpu().numpy()
+            o = {k: v.cpu().numpy() for k, v in ctx.process(dev(x), want=("frames", "iq", "mag", "phase")).items()}
+            only = ctx.process(dev(x), want=("frames",))["frames"].cpu().numpy()          # the frames-only instantiation
+            assert np.array_equal(only, o["frames"])
+            outs.append((spec, o))
+    ref = np.fft.fft(x.astype(np.float64), axis=-1)
+    for spec, o in outs:
+        assert rel_l2(spec, ref) < FFT_TOL
+    # the same butterflies in the same order; only the compiler's FMA contraction may differ between the instantiations
+    assert rel_l2(outs[0][0], outs[1][0]) < 1e-6
+    ra, ia, _ = g.decode_frame(outs[0][1]["frames"])
+    rb, ib, _ = g.decode_frame(outs[1][1]["frames"])
+    assert np.abs(ra - rb).max() <= 1 and np.abs(ia - ib).max() <= 1
+    assert ((ra != rb) | (ia != ib)).mean() < 1e-3
+    for spec, o in outs:                                                               # each variant is self-consistent
+        got = o["iq"][..., 0] + 1j * o["iq"][..., 1]
+        assert np.array_equal(cg.quantize_pack(got.astype(np.complex128), -int(np.log2(n)), 0), o["frames"])
+        _, _, mag = g.decode_frame(o["frames"])
+        assert np.array_equal(mag.view(np.uint32), o["mag"].view(np.uint32))
+
+
 def test_magnitude_averaging_in_the_pack_stage(fra, rom):
     rng = np.random.default_rng(19)
     c, n, alpha = 9, 16384, 0.125
