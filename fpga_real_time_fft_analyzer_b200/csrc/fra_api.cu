@@ -46,6 +46,11 @@ constexpr int kStreamMaxDeadband = 32;            // LSB; larger boundary differ
 constexpr int kLaneMinChannels = 28672;
 constexpr int kLaneMaxChannels = 57344;
 constexpr int kLaneBiasedMinChannels = 24576;     // k1_lane_biased from here up (measured crossover between 16384 and 32768)
+// ... and in FRA_PIPELINE mode from here up: beside the FFT of the previous call the lane kernel's lone, latency-bound warps
+// leave the FFT most of the issue slots, whereas two 96 KiB k1_duo CTAs leave an SM no room for an FFT CTA at all
+// (whole steps, ms: 12288 channels 0.659 vs 0.612 for k1_duo; 14336: 0.689 vs 0.711; 16384: 0.724 vs 0.814;
+// 20480: 0.951 vs 1.011 - profiles/r02_session4_k1_choice_pipelined.txt)
+constexpr int kLaneBiasedMinChannelsPipelined = 13312;
 
 }  // namespace
 
@@ -504,7 +509,7 @@ int process_range(fra_ctx *ctx, const int16_t *d_in, int c0, int nch, int contin
         // k1_lane_biased (whole-line staging, skewed cascade, every scheduler equally loaded) against k1_duo:
         // 32768 channels 0.82 vs 0.97 ms, 65536 1.57 vs 1.70 ms; 16384 0.56 vs 0.49 ms (too few warps per scheduler)
         if (biased && !(ctx->flags & (FRA_K1_FORCE_LANE | FRA_K1_FORCE_SPLIT | FRA_K1_FORCE_DUO)))
-            variant = (nch >= kLaneBiasedMinChannels) ? 0 : 3;
+            variant = (nch >= ((ctx->flags & FRA_PIPELINE) ? kLaneBiasedMinChannelsPipelined : kLaneBiasedMinChannels)) ? 0 : 3;
         bool alt = true;                                           // ALPHA, BETA, ALPHA, BETA, ALPHA, BETA
         for (int i = 2; i < kStages; ++i) alt = alt && std::memcmp(sec.c[i], sec.c[i & 1], 5) == 0;
         if (variant == 3) {

@@ -283,6 +283,34 @@ def test_pipeline_mode_config2_size(fra, rom):
     assert np.array_equal(st_ref[pick].cpu().numpy(), st)
 
 
+def test_pipeline_mode_four_gpu_share(fra, rom):
+    """FRA_PIPELINE at 16384 channels (config 3's share of four GPUs): the pipelined context picks the
+    lane-per-channel kernel there (the sequential one the stage-pair kernel) - same bytes from both, and the
+    filter history of a seeded subset equal to the golden model's over the concatenated stream."""
+    c, n, frames = 16384, 16384, 3
+    xs = [fra.synth.tone_noise(c, n, "cuda", frame=f) for f in range(frames)]
+    xs[1][:48] = fra.synth.full_range(48, n, "cuda", seed=5)
+    want = []
+    with fra.FraContext(c, n) as ref:
+        ref.command(0x00)
+        for i, x in enumerate(xs):
+            want.append(ref.process(x, continuous=i > 0, want=("frames",))["frames"].clone())
+        st_ref = ref.get_state().clone()
+    with fra.FraContext(c, n, flags=fra._abi.FRA_PIPELINE) as ctx:
+        ctx.command(0x00)
+        got = [ctx.process(x, continuous=i > 0, want=("frames",))["frames"] for i, x in enumerate(xs)]
+        ctx.join()
+        torch.cuda.synchronize()
+        for i in range(frames):
+            assert torch.equal(got[i], want[i]), i
+        assert torch.equal(ctx.get_state(), st_ref)
+    pick = np.array([0, 31, 47, 48, 8191, 8192, 16383])
+    st = None
+    for x in xs:
+        _, st = cg.window_iir(x[pick].cpu().numpy(), rom, 0, g.BANK0_COEFF, B1, st)
+    assert np.array_equal(st_ref[pick].cpu().numpy(), st)
+
+
 def test_command_bytes_inside_an_upload_are_data(fra, rom):
     """rx_filter_coeff's busy masking (NEW/command_control.vhd:51) on the real library: payload
     bytes that look like commands (0xFF, 0x00, 0xF1, 0xB1) are coefficients, arbitrary
