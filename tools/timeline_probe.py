@@ -4,7 +4,7 @@ FRA_PIPELINE loop sit?  Builds csrc/ with -DFRA_TIMELINE into tools/libfra_timel
 launch records its first-CTA start and last-CTA end in %globaltimer), repeats bench.py's entry
 sequence (idle, W warm-up steps, sync, K timed steps) several times in one process and prints
 the step time and the phase of the two kernels for each repetition.
-usage: timeline_probe.py [--build-only] [--reps R] [--warmup W] [--steps K]"""
+usage: timeline_probe.py [--build-only] [--reps R] [--warmup W] [--steps K] [--channels C]"""
 import argparse
 import ctypes
 import os
@@ -22,6 +22,7 @@ ap.add_argument("--build-only", action="store_true")
 ap.add_argument("--reps", type=int, default=8)
 ap.add_argument("--warmup", type=int, default=3)
 ap.add_argument("--steps", type=int, default=200)
+ap.add_argument("--channels", type=int, default=4096)
 a = ap.parse_args()
 if not os.path.exists(SO) or os.path.getmtime(SO) < os.path.getmtime(SRC):
     subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -40,7 +41,7 @@ _lib._lib = L                                   # this process only: FraContext 
 from fpga_real_time_fft_analyzer_b200 import FraContext  # noqa: E402
 
 L.fra_debug_timeline.argtypes = [ctypes.c_void_p]
-C, N = 4096, 16384
+C, N = a.channels, 16384
 ctx = FraContext(C, N, flags=_abi.FRA_PIPELINE)
 ctx.command(0x00)
 xs = [synth.tone_noise(C, N, "cuda", frame=i) for i in range(3)]
