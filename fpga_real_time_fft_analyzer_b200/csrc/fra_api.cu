@@ -328,9 +328,7 @@ int launch_k2_cluster(fra_ctx *ctx, const K2Args &args, bool win, int qmode, cud
 int launch_k2_64k(fra_ctx *ctx, const K2Args &args, bool win, int qmode, cudaStream_t st)
 {
 #ifndef FRA_HOST_EMUL
-    if (!(ctx->flags & FRA_K2_64K_SPLIT))
-        return (ctx->flags & FRA_K2_WIDE_CTA) ? launch_k2_cluster<16, 2>(ctx, args, win, qmode, st)
-                                              : launch_k2_cluster<16, 4>(ctx, args, win, qmode, st);
+    if (!(ctx->flags & FRA_K2_64K_SPLIT)) return launch_k2_cluster<16, 4>(ctx, args, win, qmode, st);
 #endif
     // scratch is indexed by the frame's position in the context, so channel slices on different
     // streams (fra_process_host) do not share it

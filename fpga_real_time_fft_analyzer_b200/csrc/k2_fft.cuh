@@ -84,10 +84,9 @@ struct FftPlan {
 // N = 32768 / 65536 across a thread-block cluster: the F = M / 4096 sub-sequences of a frame are divided over the R
 // CTAs of a cluster (FLOC = F / R each), every CTA runs its sub-FFTs locally, and the last pass reads the other
 // CTAs' sub-sequences through distributed shared memory (k2_fft_cluster below).
-//   <16, 2>: 65536 points as two CTAs of 128 KiB / 512 threads (32768 complex points are 256 KiB of fp32, more than
-//            one SM has): one CTA per SM
-//   <16, 4>: the same frame as four CTAs of 64 KiB / 256 threads: two CTAs per SM, so one CTA's passes run beside
-//            the other's loads, barriers and stores (what the 16K kernel gains from two CTAs per SM)
+//   <16, 4>: 65536 points (32768 complex points = 256 KiB of fp32, more than one SM has) as four CTAs of 64 KiB / 256
+//            threads: two CTAs per SM, so one CTA's passes run beside the other's loads, barriers and stores (what the
+//            16K kernel gains from two CTAs per SM; two CTAs of 128 KiB / 512 threads measured 249 against 274 Gsamples/s)
 //   <15, 2>: 32768 points as two CTAs of 64 KiB / 256 threads instead of one CTA of 128 KiB / 512 threads
 template <int LOG2N, int R>
 struct FftPlanCluster {
@@ -102,12 +101,11 @@ struct FftPlanCluster {
     static constexpr int FLOC = F / R;
     static constexpr int MLOC = FLOC * L;
     static constexpr int ITEMS = FLOC * NB;
-    static constexpr int THREADS = ITEMS / 2;                   // 512 (FLOC = 4) or 256 (FLOC = 2)
-    static constexpr int SMEM_BYTES = MLOC * 8;                 // 128 or 64 KiB per CTA
+    static constexpr int THREADS = ITEMS / 2;                   // 256 (FLOC = 2)
+    static constexpr int SMEM_BYTES = MLOC * 8;                 // 64 KiB per CTA (FLOC = 2)
     static constexpr int MINBLOCKS = (SMEM_BYTES <= 64 * 1024) ? 2 : 1;
     static_assert(F % R == 0 && FLOC >= 1, "cluster plan: whole sub-sequences per CTA");
 };
-using FftPlan64kCluster = FftPlanCluster<16, 2>;
 
 // two packed int16 -> two floats: one I2F.S16 each, reading the register's low / high half
 // directly (conversion unit; two issue slots per pair instead of the five of an ALU/FMA-pipe

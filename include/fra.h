@@ -93,9 +93,9 @@ typedef enum fra_status {
 #define FRA_K2_64K_SPLIT     0x400u   /* 64K frames through HBM (even / odd split, two 32K transforms, radix-2 join: 28 B of traffic per
                                         sample) instead of on chip in a cluster of two CTAs exchanging through distributed shared
                                         memory; same results within fp32 rounding, for A/B timing */
-#define FRA_K2_WIDE_CTA      0x2000u  /* 32K / 64K frames with 128 KiB / 512-thread CTAs (one per SM: 32K frames in one CTA, 64K frames in a
-                                        cluster of two) instead of 64 KiB / 256-thread CTAs in a cluster of two / four with two CTAs
-                                        per SM; same results, for A/B timing */
+#define FRA_K2_WIDE_CTA      0x2000u  /* 32K frames in one 128 KiB / 512-thread CTA (one per SM) instead of a cluster of two 64 KiB /
+                                        256-thread CTAs (two per SM) exchanging through distributed shared memory; same results
+                                        within fp32 rounding, for A/B timing */
 #define FRA_FFT_FIXED16     0x200u   /* the FFT as the 16-bit fixed-point, scaled, truncating radix-2^2 pipeline the Xilinx core is
                                         configured to be (IP/xfft_0/xfft_0.xci:12-27: 16-bit data and phase factors, scaled 1/N,
                                         truncation, natural order) instead of fp32: the spectrum carries FPGA-like quantisation

@@ -511,16 +511,17 @@ def test_64k_frames_full_chain(fra, rom):
         assert np.array_equal(host["frames"].numpy(), out["frames"])
 
 
-@pytest.mark.parametrize("n", [32768, 65536])
-def test_cluster_and_wide_cta_frames_agree(fra, rom, n):
+@pytest.mark.parametrize("n,other", [(32768, "wide"), (65536, "split")])
+def test_cluster_and_wide_cta_frames_agree(fra, rom, n, other):
     """32K / 64K frames: the default (64 KiB CTAs in a cluster of two / four, sub-sequences exchanged through
-    distributed shared memory) against FRA_K2_WIDE_CTA (128 KiB CTAs: 32K in one CTA, 64K in a cluster of two).
+    distributed shared memory) against the other path of that size - FRA_K2_WIDE_CTA (32K in one 128 KiB CTA),
+    FRA_K2_64K_SPLIT (64K as two 32K transforms through HBM).
     Both within tolerance of float64 and of each other, frames equal up to the last bit of a few bins."""
     rng = np.random.default_rng(n + 7)
     c = 7
     x = adversarial(rng, c, n)
     outs = []
-    for flags in (0, fra._abi.FRA_K2_WIDE_CTA):
+    for flags in (0, fra._abi.FRA_K2_WIDE_CTA if other == "wide" else fra._abi.FRA_K2_64K_SPLIT):
         with fra.FraContext(c, n, flags=flags) as ctx:
             spec = ctx.fft_only(dev(x)).cpu().numpy()
             o = {k: v.cpu().numpy() for k, v in ctx.process(dev(x), want=("frames", "iq", "mag", "phase")).items()}
