@@ -205,6 +205,30 @@ def test_config2_full_size_subset_and_properties(fra, rom):
         assert torch.equal(fr, want)
 
 
+def test_config2_every_sample_of_the_full_size(fra, rom):
+    """BASELINE config 2 in full - all 4096 channels x 16384 samples, not a subset: the window + IIR12 output and the
+    final history of EVERY channel bit-exact against the C golden model (67 M samples, a few seconds of one host core),
+    with full-range int16 on every 16th channel so that the wrap-around paths are exercised at size; and every
+    channel's spectrum within tolerance of a float64 FFT of its filtered frame."""
+    c, n = 4096, 16384
+    x = fra.synth.tone_noise(c, n, "cuda")
+    x[::16] = fra.synth.full_range(c // 16, n, "cuda", seed=9)
+    with fra.FraContext(c, n) as ctx:
+        ctx.command(0x00)
+        out = ctx.process(x, want=("filtered", "iq"))
+        y, st = cg.window_iir(x.cpu().numpy(), rom, 0, g.BANK0_COEFF, B1)
+        got = out["filtered"].cpu().numpy()
+        assert np.array_equal(got, y)
+        assert np.array_equal(ctx.get_state().cpu().numpy(), st)
+        for c0 in range(0, c, 512):
+            iq = out["iq"][c0:c0 + 512].cpu().numpy()
+            ref = np.fft.fft(y[c0:c0 + 512].astype(np.float64), axis=-1)
+            spec = iq[..., 0] + 1j * iq[..., 1]
+            assert rel_l2(spec, ref) < FFT_TOL, c0
+            worst = np.linalg.norm(spec - ref, axis=1) / np.linalg.norm(ref, axis=1)
+            assert worst.max() < FFT_TOL, (c0, worst.argmax())
+
+
 def test_config3_continuous_sharded_channels(fra, rom):
     """BASELINE config 3 at one GPU's share for 8 GPUs (8192 channels): IIR history
     carried across frames by the lane-per-channel kernel; splitting the stream in
@@ -254,6 +278,39 @@ def test_config3_default_dispatch_continuous(fra, rom, channels, frames):
         # every channel: the int16 frame is Hermitian (X[N-k] = conj(X[k]) up to the floor of -im)
         fr = out["frames"].view(torch.int16).view(c, n, 2)
         assert torch.equal(fr[:, 1:, 0], fr[:, 1:, 0].flip(1))
+
+
+def test_config3_every_sample_of_the_full_size(fra, rom):
+    """BASELINE config 3 in full - all 65536 continuous channels, two consecutive 16384-sample frames with the history
+    carried (2.1 G samples): window + IIR12 output of EVERY channel and the final history bit-exact against the C golden
+    model, which runs on all host cores (ctypes releases the GIL; ~25 core-seconds per frame).  Full-range int16 on
+    every 64th channel in the second frame."""
+    from concurrent.futures import ThreadPoolExecutor
+    import os
+    c, n, frames = 65536, 16384, 2
+    workers = max(1, min(32, os.cpu_count() or 1))
+    chunk = 1024
+    with fra.FraContext(c, n) as ctx:
+        ctx.command(0x00)
+        out = {"filtered": torch.empty((c, n), dtype=torch.int16, device="cuda")}
+        st = [None] * (c // chunk)
+        for f in range(frames):
+            x = fra.synth.tone_noise(c, n, "cuda", frame=f)
+            if f == 1:
+                x[::64] = fra.synth.full_range(c // 64, n, "cuda", seed=11)
+            ctx.process(x, continuous=f > 0, want=("filtered",), out=out)
+            xh = x.cpu().numpy()
+            del x
+            got = out["filtered"].cpu().numpy()
+
+            def check(i):
+                y, s_new = cg.window_iir(xh[i * chunk:(i + 1) * chunk], rom, 0, g.BANK0_COEFF, B1, st[i])
+                return i, s_new, bool(np.array_equal(got[i * chunk:(i + 1) * chunk], y))
+            with ThreadPoolExecutor(workers) as pool:
+                for i, s_new, ok in pool.map(check, range(c // chunk)):
+                    assert ok, (f, i)
+                    st[i] = s_new
+        assert np.array_equal(ctx.get_state().cpu().numpy(), np.concatenate(st, axis=0))
 
 
 def test_pipeline_mode_config2_size(fra, rom):
