@@ -340,11 +340,13 @@ def test_pipeline_mode_config2_size(fra, rom):
     assert np.array_equal(st_ref[pick].cpu().numpy(), st)
 
 
-def test_pipeline_mode_four_gpu_share(fra, rom):
-    """FRA_PIPELINE at 16384 channels (config 3's share of four GPUs): the pipelined context picks the
-    lane-per-channel kernel there (the sequential one the stage-pair kernel) - same bytes from both, and the
-    filter history of a seeded subset equal to the golden model's over the concatenated stream."""
-    c, n, frames = 16384, 16384, 3
+@pytest.mark.parametrize("c,frames", [(16384, 3), (65536, 2)])
+def test_pipeline_mode_config3_shares(fra, rom, c, frames):
+    """FRA_PIPELINE - the mode bench.py's headline runs in - at 16384 channels (config 3's share of four GPUs: the
+    pipelined context picks the lane-per-channel kernel there, the sequential one the stage-pair kernel) and at all
+    65536: same frame bytes and history as the sequential context, and the filter history of a seeded subset equal to
+    the golden model's over the concatenated stream."""
+    n = 16384
     xs = [fra.synth.tone_noise(c, n, "cuda", frame=f) for f in range(frames)]
     xs[1][:48] = fra.synth.full_range(48, n, "cuda", seed=5)
     want = []
@@ -361,7 +363,7 @@ def test_pipeline_mode_four_gpu_share(fra, rom):
         for i in range(frames):
             assert torch.equal(got[i], want[i]), i
         assert torch.equal(ctx.get_state(), st_ref)
-    pick = np.array([0, 31, 47, 48, 8191, 8192, 16383])
+    pick = np.array([0, 31, 47, 48, 8191, 8192, c - 1])
     st = None
     for x in xs:
         _, st = cg.window_iir(x[pick].cpu().numpy(), rom, 0, g.BANK0_COEFF, B1, st)
